@@ -1,0 +1,43 @@
+"""Build libdnet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+SRC = ROOT / "csrc" / "dn_api.cu"
+DEPS = [SRC, ROOT / "csrc" / "dn_kernels.cuh", ROOT.parent / "include" / "dnet_b200.h"]
+OUT = ROOT / "lib" / "libdnet_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+]
+
+
+def needs_build() -> bool:
+    if not OUT.exists():
+        return True
+    t = OUT.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    OUT.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(OUT), str(SRC)]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

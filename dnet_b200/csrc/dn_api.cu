@@ -1,0 +1,664 @@
+// dn_api.cu -- C-ABI of libdnet_b200.so (see include/dnet_b200.h).
+// Host-side bookkeeping only: which layer pointers are bound, the per-nonce paged KV,
+// scratch buffers, launch geometry, CUDA graphs, the NVLink hop and the pinned->HBM
+// layer-swap copies.  All arithmetic is in dn_kernels.cuh.
+#include "dn_kernels.cuh"
+#include "../../include/dnet_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+using namespace dn;
+
+// ---------------------------------------------------------------------------------
+// errors / options
+// ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(...)                                                                           \
+  do {                                                                                    \
+    cudaError_t e_ = (__VA_ARGS__);                                                             \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(DN_ECUDA, "%s failed: %s (%s:%d)", #__VA_ARGS__, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static std::atomic<long long> g_launches{0};
+static int g_pdl = 0;
+static int g_l2_prefetch_kb = 64;
+static int g_sms = 0;
+static int g_device = -1;
+static bool g_capturing = false;
+static long long g_capture_launches = 0;
+
+struct dn_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
+  size_t nodes = 0;
+};
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                          bool pdl_ok, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (g_pdl && pdl_ok) ? 1 : 0;
+  if (g_capturing) g_capture_launches++;
+  else g_launches++;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------
+struct LayerW {
+  const bf16* w[DN_W_COUNT];
+  bool bound = false;
+};
+
+struct dn_model {
+  dn_model_cfg cfg;
+  std::vector<int> abs_layers;
+  std::unordered_map<int, int> abs2local;
+  std::vector<LayerW> layers;
+  const bf16 *embed = nullptr, *norm = nullptr, *head = nullptr;
+  int tmax = 1, nsplit = 1, G = 1;
+  // scratch (one compute stream per model, like the reference's single compute thread)
+  bf16 *hbuf = nullptr, *qbuf = nullptr, *attn = nullptr, *act = nullptr, *logits_bf16 = nullptr;
+  float* part = nullptr;
+  unsigned int* tickets = nullptr;       // [tmax * n_kv] attention + [1] head
+  HeadPartial* head_part = nullptr;
+  float* inv_freq = nullptr;
+  StepState* null_state = nullptr;
+  // paged KV pool: [local layer][page][2][n_kv][PAGE][HD]
+  bf16* kv_pool = nullptr;
+  size_t page_elems = 0, layer_elems = 0;
+  std::vector<int> free_pages;
+  size_t max_smem = 0;
+};
+
+struct dn_kv {
+  dn_model* m = nullptr;
+  int max_tokens = 0;
+  std::vector<int> pages;
+  int32_t* block_table = nullptr;
+  StepState* st = nullptr;
+  int host_pos = 0;
+};
+
+static size_t gemv_smem(int T, int K) { return (size_t)T * K * 2 + (2 * NW * 32 + NW + 96) * sizeof(float); }
+
+template <int T, class Op>
+static cudaError_t launch_gemv(const Op& op, int units, cudaStream_t s) {
+  static bool attr_done = false;  // per instantiation
+  const size_t smem = gemv_smem(T, op.K);
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemv<T, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int grid = CTAS_PER_SM * g_sms;
+  if (grid > units) grid = units;
+  if (grid < 1) grid = 1;
+  return launch(k_gemv<T, Op>, dim3(grid), dim3(GEMV_THREADS), smem, s, true, op, g_l2_prefetch_kb * 1024);
+}
+
+template <class Op>
+static cudaError_t launch_gemv_T(int T, const Op& op, int units, cudaStream_t s) {
+  switch (T) {
+    case 1: return launch_gemv<1, Op>(op, units, s);
+    case 2: return launch_gemv<2, Op>(op, units, s);
+    case 4: return launch_gemv<4, Op>(op, units, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static cudaError_t launch_attn(dn_model* m, const bf16* q, const bf16* pool, const int32_t* bt, const StepState* st,
+                               int T, cudaStream_t s) {
+  dim3 grid(m->cfg.n_kv_heads * m->nsplit, T);
+  const int nh = m->cfg.n_heads, nkv = m->cfg.n_kv_heads, ns = m->nsplit;
+#define ATT(Gv)                                                                                          \
+  case Gv:                                                                                               \
+    return launch(k_attn<Gv>, grid, dim3(Gv * 32), 0, s, true, q, pool, bt, st, m->part, m->tickets, m->attn, nh, nkv, ns);
+  switch (m->G) {
+    ATT(1) ATT(2) ATT(4) ATT(5) ATT(7) ATT(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef ATT
+}
+
+// ---------------------------------------------------------------------------------
+// process / device
+// ---------------------------------------------------------------------------------
+extern "C" const char* dn_last_error(void) { return g_err; }
+extern "C" const char* dn_version(void) { return "dnet_b200 0.1 (sm_100a)"; }
+extern "C" int64_t dn_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int dn_device_sm_count(void) { return g_sms; }
+
+extern "C" int dn_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(DN_ECUDA, "no CUDA device visible (%s): libdnet_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(DN_EINVAL, "device %d out of range [0,%d)", device, n);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return fail(DN_EINVAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+  g_sms = p.multiProcessorCount;
+  g_device = device;
+  return DN_OK;
+}
+
+extern "C" int dn_set_option(const char* key, int64_t value) {
+  if (!key) return fail(DN_EINVAL, "null option key");
+  if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
+  return fail(DN_EINVAL, "unknown option '%s'", key);
+}
+
+// ---------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------
+extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layers, int n_layers,
+                               const float* inv_freq_host, dn_model** out) {
+  if (!cfg || !out || (n_layers > 0 && !abs_layers) || !inv_freq_host) return fail(DN_EINVAL, "null argument");
+  if (g_device < 0) return fail(DN_EINVAL, "dn_init() has not been called");
+  if (cfg->head_dim != HD) return fail(DN_EINVAL, "head_dim %d unsupported (must be 128)", cfg->head_dim);
+  if (cfg->dtype != DN_DTYPE_BF16 || cfg->wire_dtype != cfg->dtype)
+    return fail(DN_EINVAL, "only bf16 weights with a bf16 wire dtype are supported (set DNET_TRANSPORT_WIRE_DTYPE=bf16)");
+  if (cfg->hidden % 256 || cfg->ffn % 256 || (cfg->n_heads * HD) % 256)
+    return fail(DN_EINVAL, "hidden/ffn/q_dim must be multiples of 256 (got %d/%d/%d)", cfg->hidden, cfg->ffn, cfg->n_heads * HD);
+  if (cfg->n_kv_heads <= 0 || cfg->n_heads % cfg->n_kv_heads) return fail(DN_EINVAL, "n_heads must be a multiple of n_kv_heads");
+  const int G = cfg->n_heads / cfg->n_kv_heads;
+  if (!(G == 1 || G == 2 || G == 4 || G == 5 || G == 7 || G == 8)) return fail(DN_EINVAL, "GQA group %d unsupported", G);
+  if (cfg->kv_page_tokens != PAGE) return fail(DN_EINVAL, "kv_page_tokens must be %d", PAGE);
+  dn_model* m = new (std::nothrow) dn_model();
+  if (!m) return fail(DN_ENOMEM, "host allocation failed");
+  m->cfg = *cfg;
+  m->G = G;
+  for (int i = 0; i < n_layers; ++i) {
+    m->abs2local[abs_layers[i]] = i;
+    m->abs_layers.push_back(abs_layers[i]);
+  }
+  m->layers.resize(n_layers);
+  const int kmax = cfg->ffn > cfg->hidden ? cfg->ffn : cfg->hidden;
+  int tmax = 4;
+  while (tmax > 1 && gemv_smem(tmax, kmax) > 200 * 1024) tmax >>= 1;
+  m->tmax = tmax;
+  int ns = g_sms / cfg->n_kv_heads;
+  if (ns < 1) ns = 1;
+  if (ns > 32) ns = 32;
+  m->nsplit = ns;
+  const int H = cfg->hidden, qd = cfg->n_heads * HD;
+  CK(cudaMalloc(&m->hbuf, (size_t)tmax * H * 2));
+  CK(cudaMalloc(&m->qbuf, (size_t)tmax * qd * 2));
+  CK(cudaMalloc(&m->attn, (size_t)tmax * qd * 2));
+  CK(cudaMalloc(&m->act, (size_t)tmax * cfg->ffn * 2));
+  CK(cudaMalloc(&m->logits_bf16, (size_t)cfg->vocab * 2));
+  CK(cudaMalloc(&m->part, (size_t)tmax * cfg->n_heads * ns * PART_STRIDE * sizeof(float)));
+  CK(cudaMalloc(&m->tickets, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
+  CK(cudaMemset(m->tickets, 0, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
+  CK(cudaMalloc(&m->head_part, (size_t)CTAS_PER_SM * g_sms * sizeof(HeadPartial)));
+  CK(cudaMalloc(&m->inv_freq, (HD / 2) * sizeof(float)));
+  CK(cudaMemcpy(m->inv_freq, inv_freq_host, (HD / 2) * sizeof(float), cudaMemcpyHostToDevice));
+  m->page_elems = (size_t)2 * cfg->n_kv_heads * PAGE * HD;
+  m->layer_elems = m->page_elems * (size_t)cfg->kv_pool_pages;
+  if (n_layers > 0 && cfg->kv_pool_pages > 0) {
+    cudaError_t e = cudaMalloc(&m->kv_pool, m->layer_elems * n_layers * 2);
+    if (e != cudaSuccess) {
+      fail(DN_ENOMEM, "KV pool of %zu bytes: %s", m->layer_elems * n_layers * 2, cudaGetErrorString(e));
+      dn_model_destroy(m);
+      return DN_ENOMEM;
+    }
+  }
+  for (int p = cfg->kv_pool_pages - 1; p >= 0; --p) m->free_pages.push_back(p);
+  *out = m;
+  return DN_OK;
+}
+
+extern "C" int dn_model_destroy(dn_model* m) {
+  if (!m) return DN_OK;
+  cudaFree(m->hbuf); cudaFree(m->qbuf); cudaFree(m->attn); cudaFree(m->act); cudaFree(m->logits_bf16);
+  cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
+  delete m;
+  return DN_OK;
+}
+
+extern "C" int dn_model_max_chunk(dn_model* m) { return m ? m->tmax : 0; }
+
+extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_ptrs) {
+  if (!m || !dev_ptrs) return fail(DN_EINVAL, "null argument");
+  auto it = m->abs2local.find(abs_layer);
+  if (it == m->abs2local.end()) return fail(DN_ENOENT, "layer %d not hosted on this model instance", abs_layer);
+  LayerW& L = m->layers[it->second];
+  for (int i = 0; i < DN_W_COUNT; ++i) {
+    L.w[i] = static_cast<const bf16*>(dev_ptrs[i]);
+    if (i <= DN_W_LN2 && L.w[i] == nullptr) return fail(DN_EINVAL, "layer %d: tensor %d is null", abs_layer, i);
+    if (((uintptr_t)L.w[i]) & 15) return fail(DN_EINVAL, "layer %d: tensor %d is not 16-byte aligned", abs_layer, i);
+  }
+  L.bound = true;
+  return DN_OK;
+}
+
+extern "C" int dn_unbind_layer(dn_model* m, int abs_layer) {
+  if (!m) return fail(DN_EINVAL, "null argument");
+  auto it = m->abs2local.find(abs_layer);
+  if (it == m->abs2local.end()) return fail(DN_ENOENT, "layer %d not hosted on this model instance", abs_layer);
+  m->layers[it->second].bound = false;
+  memset(m->layers[it->second].w, 0, sizeof(m->layers[it->second].w));
+  return DN_OK;
+}
+
+extern "C" int dn_layer_is_bound(dn_model* m, int abs_layer) {
+  if (!m) return 0;
+  auto it = m->abs2local.find(abs_layer);
+  return (it != m->abs2local.end() && m->layers[it->second].bound) ? 1 : 0;
+}
+
+extern "C" int dn_bind_api(dn_model* m, const void* embed, const void* norm, const void* head) {
+  if (!m) return fail(DN_EINVAL, "null argument");
+  if ((((uintptr_t)embed) | ((uintptr_t)norm) | ((uintptr_t)head)) & 15) return fail(DN_EINVAL, "api tensors must be 16-byte aligned");
+  m->embed = static_cast<const bf16*>(embed);
+  m->norm = static_cast<const bf16*>(norm);
+  m->head = static_cast<const bf16*>(head);
+  if (m->cfg.tie_embeddings && !m->head) m->head = m->embed;
+  return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// per-nonce KV
+// ---------------------------------------------------------------------------------
+extern "C" int dn_kv_create(dn_model* m, int max_tokens, dn_kv** out) {
+  if (!m || !out || max_tokens <= 0) return fail(DN_EINVAL, "bad argument");
+  const int np = (max_tokens + PAGE - 1) / PAGE;
+  if ((int)m->free_pages.size() < np)
+    return fail(DN_ENOSPC, "KV pool exhausted: need %d pages, %zu free", np, m->free_pages.size());
+  dn_kv* kv = new (std::nothrow) dn_kv();
+  if (!kv) return fail(DN_ENOMEM, "host allocation failed");
+  kv->m = m;
+  kv->max_tokens = np * PAGE;
+  for (int i = 0; i < np; ++i) { kv->pages.push_back(m->free_pages.back()); m->free_pages.pop_back(); }
+  CK(cudaMalloc(&kv->block_table, (size_t)np * sizeof(int32_t)));
+  CK(cudaMemcpy(kv->block_table, kv->pages.data(), (size_t)np * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&kv->st, sizeof(StepState)));
+  CK(cudaMemset(kv->st, 0, sizeof(StepState)));
+  *out = kv;
+  return DN_OK;
+}
+
+extern "C" int dn_kv_free(dn_kv* kv) {
+  if (!kv) return DN_OK;
+  for (int p : kv->pages) kv->m->free_pages.push_back(p);
+  cudaFree(kv->block_table);
+  cudaFree(kv->st);
+  delete kv;
+  return DN_OK;
+}
+
+extern "C" int dn_kv_offset(dn_kv* kv) { return kv ? kv->host_pos : -1; }
+extern "C" void* dn_kv_token_ptr(dn_kv* kv) { return kv ? (void*)&kv->st->token : nullptr; }
+
+extern "C" int dn_kv_reset(dn_kv* kv, dn_stream s) {
+  if (!kv) return fail(DN_EINVAL, "null kv");
+  CK(launch(k_set_state, dim3(1), dim3(32), 0, (cudaStream_t)s, false, kv->st, 0, 0, 1, 0));
+  kv->host_pos = 0;
+  return DN_OK;
+}
+
+extern "C" int dn_kv_advance(dn_kv* kv, int T, dn_stream s) {
+  if (!kv || T < 0) return fail(DN_EINVAL, "bad argument");
+  CK(launch(k_advance, dim3(1), dim3(32), 0, (cudaStream_t)s, true, kv->st, T));
+  if (!g_capturing) kv->host_pos += T;
+  return DN_OK;
+}
+
+extern "C" int dn_kv_seek(dn_kv* kv, int pos, dn_stream s) {
+  if (!kv || pos < 0 || pos > kv->max_tokens) return fail(DN_EINVAL, "bad seek position");
+  CK(launch(k_set_state, dim3(1), dim3(32), 0, (cudaStream_t)s, false, kv->st, pos, 0, 1, 0));
+  if (!g_capturing) kv->host_pos = pos;
+  return DN_OK;
+}
+
+extern "C" int dn_kv_set_token(dn_kv* kv, int32_t token, dn_stream s) {
+  if (!kv) return fail(DN_EINVAL, "null kv");
+  CK(launch(k_set_state, dim3(1), dim3(32), 0, (cudaStream_t)s, false, kv->st, 0, (int)token, 0, 1));
+  return DN_OK;
+}
+
+// host mirror bookkeeping for graph replays (a replay advances the device offset by the
+// captured T without passing through dn_kv_advance)
+extern "C" int dn_kv_note_advance(dn_kv* kv, int T) {
+  if (!kv) return fail(DN_EINVAL, "null kv");
+  kv->host_pos += T;
+  return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------------
+extern "C" int dn_embed(dn_model* m, const int32_t* ids_dev, int T, void* x_out, dn_stream s) {
+  if (!m || !ids_dev || !x_out || T <= 0) return fail(DN_EINVAL, "bad argument");
+  if (!m->embed) return fail(DN_ENOENT, "embed_tokens not bound on this shard");
+  CK(launch(k_embed, dim3(T), dim3(256), 0, (cudaStream_t)s, true, ids_dev, m->embed, (bf16*)x_out, m->cfg.hidden, m->cfg.vocab));
+  return DN_OK;
+}
+
+static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, cudaStream_t s, cudaEvent_t* evs = nullptr) {
+  auto it = m->abs2local.find(abs_layer);
+  if (it == m->abs2local.end()) return fail(DN_ENOENT, "Layer %d not hosted on this model instance", abs_layer);
+  const int li = it->second;
+  const LayerW& L = m->layers[li];
+  if (!L.bound) return fail(DN_ENOENT, "layer %d has no weights bound", abs_layer);
+  const dn_model_cfg& c = m->cfg;
+  const int H = c.hidden, qd = c.n_heads * HD;
+  bf16* pool = m->kv_pool + (size_t)li * m->layer_elems;
+
+  OpQKV q;
+  q.K = H; q.nrows = (c.n_heads + 2 * c.n_kv_heads) * HD;
+  q.x = x; q.ln_w = L.w[DN_W_LN1];
+  q.wq = L.w[DN_W_Q]; q.wk = L.w[DN_W_K]; q.wv = L.w[DN_W_V];
+  q.bq = L.w[DN_W_QB]; q.bk = L.w[DN_W_KB]; q.bv = L.w[DN_W_VB];
+  q.q_out = m->qbuf; q.kv_pool = pool; q.block_table = kv->block_table; q.st = kv->st;
+  q.inv_freq = m->inv_freq; q.n_heads = c.n_heads; q.n_kv = c.n_kv_heads; q.eps = c.rms_eps;
+  if (evs) CK(cudaEventRecord(evs[0], s));
+  CK(launch_gemv_T(T, q, q.nrows / 2, s));
+  if (evs) CK(cudaEventRecord(evs[1], s));
+
+  CK(launch_attn(m, m->qbuf, pool, kv->block_table, kv->st, T, s));
+  if (evs) CK(cudaEventRecord(evs[2], s));
+
+  OpOProj o;
+  o.K = qd; o.nrows = H; o.a = m->attn; o.w = L.w[DN_W_O]; o.resid = x; o.out = m->hbuf;
+  CK(launch_gemv_T(T, o, o.nrows, s));
+  if (evs) CK(cudaEventRecord(evs[3], s));
+
+  OpGateUp g;
+  g.K = H; g.nrows = 2 * c.ffn; g.x = m->hbuf; g.ln_w = L.w[DN_W_LN2];
+  g.wg = L.w[DN_W_GATE]; g.wu = L.w[DN_W_UP]; g.act = m->act; g.eps = c.rms_eps;
+  CK(launch_gemv_T(T, g, c.ffn, s));
+  if (evs) CK(cudaEventRecord(evs[4], s));
+
+  OpDown d;
+  d.K = c.ffn; d.nrows = H; d.a = m->act; d.w = L.w[DN_W_DOWN]; d.resid = m->hbuf; d.out = x;
+  CK(launch_gemv_T(T, d, d.nrows, s));
+  if (evs) CK(cudaEventRecord(evs[5], s));
+  return DN_OK;
+}
+
+static int head_common(dn_model* m, const void* x, int T, dn_kv* kv, int32_t* token_out, float* logprob_out,
+                       float* logits_f32, cudaStream_t s);
+
+static int check_fwd(dn_model* m, void* x, int T, dn_kv* kv) {
+  if (!m || !x || !kv) return fail(DN_EINVAL, "null argument");
+  if (kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
+  if (!(T == 1 || T == 2 || T == 4) || T > m->tmax) return fail(DN_EINVAL, "T=%d unsupported (1,2,4 up to %d)", T, m->tmax);
+  if (!g_capturing && kv->host_pos + T > kv->max_tokens)
+    return fail(DN_ENOSPC, "KV capacity exceeded: offset %d + %d > %d", kv->host_pos, T, kv->max_tokens);
+  if (((uintptr_t)x) & 15) return fail(DN_EINVAL, "activation must be 16-byte aligned");
+  return DN_OK;
+}
+
+extern "C" int dn_layer_forward(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s) {
+  int rc = check_fwd(m, x_inout, T, kv);
+  if (rc) return rc;
+  return layer_forward(m, abs_layer, (bf16*)x_inout, T, kv, (cudaStream_t)s);
+}
+
+// Per-kernel device times of one layer (CUDA events between the five launches, on the
+// launching stream; PDL is off for this call so each kernel is timed alone).  Used by
+// bench.py for the live roofline numerator; synchronises the stream.
+extern "C" int dn_layer_forward_timed(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s,
+                                      float ms_out[5]) {
+  int rc = check_fwd(m, x_inout, T, kv);
+  if (rc) return rc;
+  if (!ms_out) return fail(DN_EINVAL, "null ms_out");
+  if (g_capturing) return fail(DN_EINVAL, "cannot time inside a graph capture");
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&ev[i]));
+  const int pdl = g_pdl;
+  g_pdl = 0;
+  rc = layer_forward(m, abs_layer, (bf16*)x_inout, T, kv, (cudaStream_t)s, ev);
+  g_pdl = pdl;
+  if (rc == DN_OK) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)s);
+    if (e != cudaSuccess) rc = fail(DN_ECUDA, "sync: %s", cudaGetErrorString(e));
+  }
+  if (rc == DN_OK)
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
+// same for the fused final-norm + lm_head + greedy-sample kernel
+extern "C" int dn_head_timed(dn_model* m, const void* x, int T, dn_stream s, float* ms_out) {
+  if (!ms_out) return fail(DN_EINVAL, "null ms_out");
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int pdl = g_pdl;
+  g_pdl = 0;
+  CK(cudaEventRecord(a, (cudaStream_t)s));
+  int rc = head_common(m, x, T, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)s);
+  g_pdl = pdl;
+  if (rc) return rc;
+  CK(cudaEventRecord(b, (cudaStream_t)s));
+  CK(cudaStreamSynchronize((cudaStream_t)s));
+  CK(cudaEventElapsedTime(ms_out, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return DN_OK;
+}
+
+extern "C" int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, int T, dn_kv* kv, dn_stream s) {
+  int rc = check_fwd(m, x_inout, T, kv);
+  if (rc) return rc;
+  if (n > 0 && !abs_layers) return fail(DN_EINVAL, "null layer list");
+  for (int i = 0; i < n; ++i) {
+    rc = layer_forward(m, abs_layers[i], (bf16*)x_inout, T, kv, (cudaStream_t)s);
+    if (rc) return rc;
+  }
+  return DN_OK;
+}
+
+static int head_common(dn_model* m, const void* x, int T, dn_kv* kv, int32_t* token_out, float* logprob_out,
+                       float* logits_f32, cudaStream_t s) {
+  if (!m || !x || T <= 0) return fail(DN_EINVAL, "bad argument");
+  if (!m->norm || !m->head) return fail(DN_ENOENT, "final norm / lm_head not bound on this shard");
+  OpHead h;
+  h.K = m->cfg.hidden; h.nrows = m->cfg.vocab;
+  h.x = (const bf16*)x + (size_t)(T - 1) * m->cfg.hidden;  // last position only (result-identical)
+  h.ln_w = m->norm; h.w = m->head; h.logits_bf16 = m->logits_bf16; h.logits_f32 = logits_f32;
+  h.partials = m->head_part; h.ticket = m->tickets + (size_t)m->tmax * m->cfg.n_kv_heads;
+  h.token_out = token_out; h.logprob_out = logprob_out; h.st = kv ? kv->st : nullptr; h.eps = m->cfg.rms_eps;
+  CK(launch_gemv<1, OpHead>(h, h.nrows, s));
+  return DN_OK;
+}
+
+extern "C" int dn_head_sample_greedy(dn_model* m, const void* x, int T, dn_kv* kv, int32_t* token_out,
+                                     float* logprob_out, dn_stream s) {
+  return head_common(m, x, T, kv, token_out, logprob_out, nullptr, (cudaStream_t)s);
+}
+
+extern "C" int dn_head_logits(dn_model* m, const void* x, int T, float* logits_f32_out, void* logits_bf16_out, dn_stream s) {
+  int rc = head_common(m, x, T, nullptr, nullptr, nullptr, logits_f32_out, (cudaStream_t)s);
+  if (rc) return rc;
+  if (logits_bf16_out)
+    CK(cudaMemcpyAsync(logits_bf16_out, m->logits_bf16, (size_t)m->cfg.vocab * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// graphs
+// ---------------------------------------------------------------------------------
+extern "C" int dn_graph_begin(dn_stream s) {
+  if (g_capturing) return fail(DN_EINVAL, "a capture is already in progress");
+  CK(cudaStreamBeginCapture((cudaStream_t)s, cudaStreamCaptureModeThreadLocal));
+  g_capturing = true;
+  g_capture_launches = 0;
+  return DN_OK;
+}
+
+extern "C" int dn_graph_end(dn_stream s, dn_graph** out) {
+  if (!g_capturing) return fail(DN_EINVAL, "no capture in progress");
+  g_capturing = false;
+  dn_graph* g = new (std::nothrow) dn_graph();
+  if (!g) return fail(DN_ENOMEM, "host allocation failed");
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)s, &g->graph);
+  if (e != cudaSuccess || !g->graph) { delete g; return fail(DN_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e)); }
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g->graph); delete g; return fail(DN_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  g->kernels = g_capture_launches;
+  cudaGraphGetNodes(g->graph, nullptr, &g->nodes);
+  *out = g;
+  return DN_OK;
+}
+
+extern "C" int dn_graph_launch(dn_graph* g, dn_stream s) {
+  if (!g) return fail(DN_EINVAL, "null graph");
+  CK(cudaGraphLaunch(g->exec, (cudaStream_t)s));
+  g_launches += g->kernels;
+  return DN_OK;
+}
+
+extern "C" int dn_graph_destroy(dn_graph* g) {
+  if (!g) return DN_OK;
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
+  return DN_OK;
+}
+
+extern "C" int dn_graph_num_nodes(dn_graph* g) { return g ? (int)g->nodes : 0; }
+
+// ---------------------------------------------------------------------------------
+// ring hop
+// ---------------------------------------------------------------------------------
+extern "C" int dn_hop_alloc(size_t bytes, void** dev_ptr) {
+  if (!dev_ptr || bytes == 0) return fail(DN_EINVAL, "bad argument");
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return fail(DN_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  CK(cudaMemset(*dev_ptr, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  return DN_OK;
+}
+extern "C" int dn_hop_free(void* p) { if (p) CK(cudaFree(p)); return DN_OK; }
+extern "C" int dn_hop_export(void* dev_ptr, uint8_t handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle_out, &h, 64);
+  return DN_OK;
+}
+extern "C" int dn_hop_import(const uint8_t handle[64], void** dev_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DN_OK;
+}
+extern "C" int dn_hop_close(void* p) { if (p) CK(cudaIpcCloseMemHandle(p)); return DN_OK; }
+extern "C" int dn_enable_peer(int peer) {
+  int can = 0;
+  CK(cudaDeviceCanAccessPeer(&can, g_device, peer));
+  if (!can) return fail(DN_EINVAL, "device %d cannot access peer %d", g_device, peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return DN_OK; }
+  CK(e);
+  return DN_OK;
+}
+extern "C" int dn_hop_send(void* dst_slot, const void* src, size_t bytes, uint32_t* dst_flag, uint32_t seq, dn_stream s) {
+  if (!dst_slot || !src || !dst_flag) return fail(DN_EINVAL, "null argument");
+  CK(cudaMemcpyAsync(dst_slot, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  CK(launch(k_flag_set, dim3(1), dim3(32), 0, (cudaStream_t)s, false, dst_flag, seq));
+  return DN_OK;
+}
+extern "C" int dn_hop_wait(const uint32_t* flag, uint32_t seq, uint32_t timeout_ms, uint32_t* err_flag, dn_stream s) {
+  if (!flag) return fail(DN_EINVAL, "null argument");
+  CK(launch(k_flag_wait, dim3(1), dim3(32), 0, (cudaStream_t)s, false, flag, seq,
+            (unsigned long long)timeout_ms * 1000000ull, err_flag));
+  return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// layer swap / plumbing
+// ---------------------------------------------------------------------------------
+extern "C" int dn_pinned_alloc(size_t bytes, void** host_ptr) {
+  if (!host_ptr || bytes == 0) return fail(DN_EINVAL, "bad argument");
+  cudaError_t e = cudaHostAlloc(host_ptr, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) return fail(DN_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return DN_OK;
+}
+extern "C" int dn_pinned_free(void* p) { if (p) CK(cudaFreeHost(p)); return DN_OK; }
+extern "C" int dn_device_alloc(size_t bytes, void** dev_ptr) {
+  if (!dev_ptr || bytes == 0) return fail(DN_EINVAL, "bad argument");
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return fail(DN_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return DN_OK;
+}
+extern "C" int dn_device_free(void* p) { if (p) CK(cudaFree(p)); return DN_OK; }
+extern "C" int dn_slot_prefetch(void* dst_dev, const void* src_pinned, size_t bytes, dn_stream prefetch, dn_event done) {
+  if (!dst_dev || !src_pinned) return fail(DN_EINVAL, "null argument");
+  CK(cudaMemcpyAsync(dst_dev, src_pinned, bytes, cudaMemcpyHostToDevice, (cudaStream_t)prefetch));
+  if (done) CK(cudaEventRecord((cudaEvent_t)done, (cudaStream_t)prefetch));
+  return DN_OK;
+}
+extern "C" int dn_stream_create(dn_stream* out, int high_priority) {
+  if (!out) return fail(DN_EINVAL, "null argument");
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  cudaStream_t s;
+  CK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+  *out = s;
+  return DN_OK;
+}
+extern "C" int dn_stream_destroy(dn_stream s) { CK(cudaStreamDestroy((cudaStream_t)s)); return DN_OK; }
+extern "C" int dn_stream_sync(dn_stream s) { CK(cudaStreamSynchronize((cudaStream_t)s)); return DN_OK; }
+extern "C" int dn_stream_wait_event(dn_stream s, dn_event e) { CK(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return DN_OK; }
+extern "C" int dn_event_create(dn_event* out, int timing) {
+  if (!out) return fail(DN_EINVAL, "null argument");
+  cudaEvent_t e;
+  CK(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+  *out = e;
+  return DN_OK;
+}
+extern "C" int dn_event_destroy(dn_event e) { CK(cudaEventDestroy((cudaEvent_t)e)); return DN_OK; }
+extern "C" int dn_event_record(dn_event e, dn_stream s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return DN_OK; }
+extern "C" int dn_event_query(dn_event e) {
+  cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+  if (r == cudaSuccess) return 1;
+  if (r == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  return fail(DN_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(r));
+}
+extern "C" int dn_event_sync(dn_event e) { CK(cudaEventSynchronize((cudaEvent_t)e)); return DN_OK; }
+extern "C" int dn_event_elapsed_ms(dn_event a, dn_event b, float* ms) {
+  CK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return DN_OK;
+}
+extern "C" int dn_memcpy_h2d(void* dst, const void* src, size_t bytes, dn_stream s) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+  return DN_OK;
+}
+extern "C" int dn_memcpy_d2h(void* dst, const void* src, size_t bytes, dn_stream s) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  return DN_OK;
+}

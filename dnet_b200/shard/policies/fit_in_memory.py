@@ -1,0 +1,186 @@
+"""``fit`` policy: everything resident (reference src/dnet/shard/policies/fit_in_memory.py:15-236),
+driving libdnet_b200 instead of MLX.
+
+Differences that are deliberate and result-identical:
+  * the per-layer Python loop + ``mx.eval`` per window is one ``dn_window_forward`` call
+    (or, for single-token messages, one CUDA-graph replay of the whole shard step);
+  * the per-layer cast to the wire dtype is the bf16 store of the down-proj epilogue;
+  * the end shard projects the last position only and, at temperature 0, the argmax /
+    logsumexp are fused into the lm_head kernel.
+Conventions kept: runs on the compute thread under ``runtime._model_lock``; never raises;
+releases the input buffer; emits exactly one output message per input on success.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from dnet_b200 import _cabi
+from dnet_b200.core.memory.weight_cache import WeightCache
+from dnet_b200.core.types.messages import ActivationMessage, TokenResult
+from dnet_b200.utils.logger import logger
+from . import _cuda_common as cc
+from .base import ComputePolicy, register_policy
+
+
+@register_policy("fit")
+class FitInMemoryPolicy(ComputePolicy):
+    """Everything fits - no offloading needed"""
+
+    def configure_policy_for_model(self, req) -> None:
+        self._mode = "fit"
+        local_count = max(1, len(self.runtime.assigned_layers))
+        requested_w = max(1, int(req.window_size))
+        self.window_size = min(local_count, requested_w)
+        self.weight_cache = WeightCache(
+            self.runtime.assigned_layers,
+            self.runtime.model_metadata,
+            window_size=self.window_size,
+            prefetch_threads=self.runtime.prefetch_threads,
+            resident_windows=self._resident_windows,
+            use_mxload_fastpath=self.runtime.compute_config.mxload_fastpath,
+            prefetch_mode=self.runtime.compute_config.prefetch_mode,
+            stage_host=self.runtime.stage_host,
+        )
+
+    # -- CUDA-graph fast path for single-token messages ----------------------------------
+    def _graph_step(self, ns, x, is_tokens: bool, run: list[int], fused_head: bool) -> None:
+        """Replay (capturing on first use) [embed] + window + [norm/head/argmax] + advance."""
+        rt = self.runtime
+        lib = _cabi.load()
+        s = rt.compute_stream_ptr
+        key = (run[0], is_tokens, fused_head)
+        g = ns.graphs.get(key)
+        if g is None:
+            rt.compute_stream.synchronize()
+            _cabi.check(lib.dn_graph_begin(s))
+            gp = C.c_void_p()
+            try:
+                if is_tokens:
+                    _cabi.check(lib.dn_embed(rt.model._h, ns.kv.token_ptr, 1, x.data_ptr(), s))
+                arr = (C.c_int32 * len(run))(*run)
+                _cabi.check(lib.dn_window_forward(rt.model._h, arr, len(run), x.data_ptr(), 1, ns.kv._h, s))
+                if fused_head:
+                    _cabi.check(lib.dn_head_sample_greedy(rt.model._h, x.data_ptr(), 1, ns.kv._h,
+                                                          ns.result_token_ptr, ns.result_logprob_ptr, s))
+                _cabi.check(lib.dn_kv_advance(ns.kv._h, 1, s))
+            finally:
+                rc = lib.dn_graph_end(s, C.byref(gp))
+            _cabi.check(rc)
+            g = gp.value
+            ns.graphs[key] = g
+        _cabi.check(lib.dn_graph_launch(g, s))
+        ns.kv.note_advance(1)
+
+    def process(self, msg: ActivationMessage) -> None:
+        rt = self.runtime
+        try:
+            with rt._model_lock:
+                if not cc.model_ready(rt):
+                    logger.error("Runtime %s: cannot process activation - model not loaded", rt.shard_id)
+                    return
+                # 1) per-nonce KV (+ activation buffer, captured graphs, pinned result)
+                ns = rt.get_or_make_kv(msg.nonce)
+                T = cc.msg_tokens(rt, msg)
+                current_layer = msg.layer_id + 1
+                run = cc.local_run(rt, current_layer)
+                if not run or T <= 0:
+                    logger.error("layer %s not hosted on shard %s (or empty message)", current_layer, rt.shard_id)
+                    rt.input_pool.release(msg.pool_id)
+                    return
+                if ns.kv.offset + T > ns.kv.max_tokens:
+                    logger.error("KV capacity exceeded for nonce %s: %d + %d > %d", msg.nonce, ns.kv.offset, T,
+                                 ns.kv.max_tokens)
+                    rt.input_pool.release(msg.pool_id)
+                    return
+                last_layer = run[-1]
+                is_end = last_layer + 1 >= rt.model_metadata.num_layers
+                greedy = msg.temperature == 0 and msg.req_top_logprobs <= 0
+
+                # 2) bind (fast exit when everything is already bound)
+                to_bind = self._bind_layer_weights(run, msg)
+                if to_bind is None:
+                    return
+                rt._compute_busy.set()
+                if to_bind:
+                    cc.wait_layers_ready(rt, self.weight_cache, run)
+                    rt.model.load_weights(list(to_bind.items()), strict=False)
+                    for other in rt.all_nonce_states():
+                        other.drop_graphs()
+
+                # 3) stage x, 4) compute the run
+                final = None
+                use_graph = rt.use_cuda_graphs and T == 1 and self.window_size >= len(run)
+                if use_graph:
+                    is_tokens = msg.dtype == "tokens"
+                    if is_tokens:
+                        buf = rt.input_pool.get_buffer(msg.pool_id)
+                        if buf is None:
+                            logger.error("Failed to get input buffer %s", msg.pool_id)
+                            return
+                        ns.kv.set_token(int(buf[0]), rt.compute_stream_ptr)
+                        x = ns.x_view(1)
+                    else:
+                        staged = cc.stage_input(rt, msg, ns)
+                        if staged is None:
+                            logger.error("Failed to get input buffer %s", msg.pool_id)
+                            return
+                        x = staged[0]
+                    self._graph_step(ns, x, is_tokens, run, is_end and greedy)
+                    for lid in run:
+                        self.weight_cache.decrease_reference(lid)
+                    if is_end and greedy:
+                        rt.compute_stream.synchronize()
+                        final = TokenResult(token_id=int(ns.result_i32[0].item()),
+                                            logprob=float(ns.result_f32[1].item()) if msg.req_logprobs else 0.0,
+                                            top_logprobs={})
+                else:
+                    staged = cc.stage_input(rt, msg, ns)
+                    if staged is None:
+                        logger.error("Failed to get input buffer %s", msg.pool_id)
+                        return
+                    x = staged[0]
+                    for w0 in range(0, len(run), self.window_size):
+                        window_layers = run[w0:w0 + self.window_size]
+                        rt.model.window_forward(window_layers, x, ns.kv, rt.compute_stream_ptr)
+                        for lid in window_layers:
+                            self.weight_cache.decrease_reference(lid)
+                    ns.kv.advance(T, rt.compute_stream_ptr)
+                if is_end and final is None:
+                    try:
+                        final = cc.sample_end_shard(rt, msg, ns, x)
+                    except Exception as e:
+                        logger.error("End-shard sampling failed: %s", e)
+                        rt.input_pool.release(msg.pool_id)
+                        return
+                output_msg = cc.build_output(rt, msg, x, last_layer, final)
+                rt.emit_result(output_msg)
+                rt.input_pool.release(msg.pool_id)
+                return
+        except Exception as e:
+            logger.exception("Error in fit policy process: %s", e)
+            try:
+                if rt.input_pool:
+                    rt.input_pool.release(msg.pool_id)
+            except Exception:
+                pass
+        finally:
+            try:
+                rt._compute_busy.clear()
+            except Exception:
+                pass
+
+    def clear(self):
+        try:
+            if self.weight_cache:
+                self.weight_cache.cancel_all_prefetch()
+        except Exception:
+            pass
+        for layer_id in list(self._bound_versions.keys()):
+            try:
+                self.weight_cache.evict_layer(layer_id)
+            except Exception:
+                pass
+        try:
+            self._bound_versions.clear()
+        except Exception:
+            self._bound_versions = {}

@@ -1,0 +1,324 @@
+"""ShardRuntime: owns model, per-nonce KV, pools, policy and the local ingress -> compute ->
+egress queues (reference src/dnet/shard/runtime.py:56-401), rebuilt over CUDA streams.
+
+No ring, no gRPC, no discovery: submit(ActivationMessage) -> ActivationMessage.
+Threading model preserved: one compute thread drains ``activation_recv_queue`` and calls
+``policy.process``; a 4-thread executor serves deserialisation / prefetch helpers.
+"""
+from __future__ import annotations
+
+import asyncio
+import gc
+import queue
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from queue import Queue
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from dnet_b200 import _cabi
+from dnet_b200.config import get_settings
+from dnet_b200.core.memory.memory_pool import LayerAwareMemoryPool
+from dnet_b200.core.models import BaseRingModel, KVHandle, get_ring_model
+from dnet_b200.core.types.messages import ActivationMessage
+from dnet_b200.utils.logger import logger
+from dnet_b200.utils.model import ModelMetadata, SyntheticSource, get_model_metadata, load_weight
+from .models import ShardLoadModelRequest, ShardUnloadModelResponse
+from .policies import ComputePolicy, NoopPolicy, PolicyPlan, make_policy, plan_policy
+
+
+class RuntimeKVCacheConfig:
+    def __init__(self, settings):
+        self.mode: str = settings.mode
+        self.bits: int = settings.bits
+        self.group_size: int = settings.group_size
+        self.kv_ttl_s: float = settings.ttl_s
+        self.max_tokens: int = settings.max_tokens
+
+
+class RuntimeComputeConfig:
+    def __init__(self, settings):
+        self.prefetch_mode: str = settings.prefetch_mode
+        self.mxload_fastpath: bool = settings.mxload_fastpath
+        self.input_pool_mb: int = settings.input_pool_mb
+        self.output_pool_mb: int = settings.output_pool_mb
+
+
+class NonceState:
+    """Everything a nonce owns on this shard: paged KV handle, its HBM activation buffer,
+    device token-id staging, the pinned (token, logprob) result and captured step graphs."""
+
+    def __init__(self, model: BaseRingModel, max_tokens: int):
+        self.kv = KVHandle(model, max_tokens)
+        self._model = model
+        self._x: Optional[torch.Tensor] = None
+        self._ids: Optional[torch.Tensor] = None
+        self.graphs: Dict[Any, int] = {}
+        self.keepalive = None
+        res = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.result_i32 = res
+        self.result_f32 = res.view(torch.float32)
+        self.result_token_ptr = res.data_ptr()
+        self.result_logprob_ptr = res.data_ptr() + 4
+        self.x1 = torch.zeros(1, model.hidden_size, dtype=torch.bfloat16, device="cuda")  # stable graph address
+
+    def x_view(self, T: int) -> torch.Tensor:
+        if T == 1:
+            return self.x1
+        if self._x is None or self._x.shape[0] < T:
+            self._x = torch.empty(T, self._model.hidden_size, dtype=torch.bfloat16, device="cuda")
+        return self._x[:T]
+
+    def ids_view(self, T: int) -> torch.Tensor:
+        if self._ids is None or self._ids.numel() < T:
+            self._ids = torch.empty(max(T, 16), dtype=torch.int32, device="cuda")
+        return self._ids[:T]
+
+    def drop_graphs(self) -> None:
+        lib = _cabi.load()
+        for g in self.graphs.values():
+            lib.dn_graph_destroy(g)
+        self.graphs.clear()
+
+    def free(self) -> None:
+        self.drop_graphs()
+        self.kv.free()
+
+
+class ShardRuntime:
+    """Topology-agnostic shard runtime."""
+
+    def __init__(self, shard_id, queue_size: int = 128, device_prefetch_workers: int = 4, prefetch_threads: int = 2):
+        self.shard_id = shard_id
+        settings = get_settings()
+        self._compute_settings = settings.compute
+        self._transport_settings = settings.transport
+        self._topology_settings = settings.topology
+        self.kv_cache_config = RuntimeKVCacheConfig(settings.kv_cache)
+        self._compute_config = RuntimeComputeConfig(settings.compute)
+        self.policy: ComputePolicy = NoopPolicy(runtime=self, resident_windows=1)
+        self._device_prefetch_workers = device_prefetch_workers
+        self.prefetch_threads = prefetch_threads
+        self._loop: Optional[asyncio.AbstractEventLoop] = None
+        self.max_queue_size = queue_size
+        self.activation_recv_queue: Queue[ActivationMessage] = Queue(maxsize=queue_size)
+        self.activation_send_queue: Queue[ActivationMessage] = Queue(maxsize=queue_size)
+        self.compute_thread: Optional[threading.Thread] = None
+        self.running = False
+        self.executor = ThreadPoolExecutor(max_workers=int(self._device_prefetch_workers or 4))
+        self.assigned_layers: List[int] = []
+        self._assigned_sorted: List[int] = []
+        self._assigned_set: set = set()
+        self.model_metadata: Optional[ModelMetadata] = None
+        self.model: Optional[BaseRingModel] = None
+        self.cache: Optional[Any] = None
+        self.model_path: Optional[Any] = None
+        self.input_pool: Optional[LayerAwareMemoryPool] = None
+        self.output_pool: Optional[LayerAwareMemoryPool] = None
+        _wd = (self._transport_settings.wire_dtype or "fp16").strip().lower()
+        self._wire_dtype_str = "bfloat16" if _wd in {"bf16", "bfloat16"} else "float16"
+        self._wire_mx_dtype = torch.bfloat16 if self._wire_dtype_str == "bfloat16" else torch.float16
+        self._compute_busy = threading.Event()
+        self._mlx_lock = threading.Lock()  # name kept for drop-in parity; guards C-ABI calls
+        self._model_lock = threading.Lock()
+        self._kv_by_nonce: Dict[str, NonceState] = {}
+        self._kv_last_seen: Dict[str, float] = {}
+        self._kv_ttl_s: float = self.kv_cache_config.kv_ttl_s
+        # CUDA plumbing
+        self.compute_stream: Optional[torch.cuda.Stream] = None
+        self.compute_stream_ptr: int = 0
+        self.use_cuda_graphs: bool = bool(self._compute_settings.cuda_graphs)
+        self.stage_host: bool = True
+        self._api_tensors: Dict[str, torch.Tensor] = {}
+
+    @property
+    def compute_config(self):
+        return self._compute_config
+
+    @property
+    def transport_config(self):
+        return self._transport_settings
+
+    @property
+    def topology_config(self):
+        return self._topology_settings
+
+    def attach_loop(self, loop):
+        self._loop = loop
+
+    def queue_size(self) -> int:
+        return self.activation_recv_queue.qsize()
+
+    def emit_result(self, msg: ActivationMessage) -> None:
+        self.activation_send_queue.put_nowait(msg)
+
+    def all_nonce_states(self):
+        return list(self._kv_by_nonce.values())
+
+    def shutdown(self) -> None:
+        self.running = False
+        if self.compute_thread:
+            try:
+                self.compute_thread.join(timeout=5)
+            except Exception:
+                pass
+            self.compute_thread = None
+        self.executor.shutdown(wait=True, cancel_futures=True)
+        for ns in self._kv_by_nonce.values():
+            ns.free()
+        self._kv_by_nonce.clear()
+        self._kv_last_seen.clear()
+
+    # -- model load ------------------------------------------------------------------------
+    def load_model_core(self, req: ShardLoadModelRequest) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("dnet_b200 needs a CUDA device: the shard forward has no CPU fallback")
+        _cabi.init(torch.cuda.current_device())
+        if self._wire_dtype_str != "bfloat16":
+            raise ValueError("set DNET_TRANSPORT_WIRE_DTYPE=bf16: the wire dtype must equal the bf16 model dtype")
+        lib = _cabi.load()
+        lib.dn_set_option(b"pdl", 1 if self._compute_settings.pdl else 0)
+        self.model_metadata = get_model_metadata(req.model_path)
+        self.assigned_layers = list(req.layers)
+        self._assigned_sorted = sorted(self.assigned_layers)
+        self._assigned_set = set(self._assigned_sorted)
+        self.model_path = req.model_path
+        local_count = max(1, len(self.assigned_layers))
+        plan: PolicyPlan = plan_policy(local_count=local_count, requested_w=int(req.window_size),
+                                       residency_size=int(req.residency_size), topology_config=self._topology_settings)
+        kv = (req.kv_bits or "").strip().lower()
+        if kv in ("4bit", "8bit"):
+            raise NotImplementedError("quantised KV (kv_bits 4bit/8bit) is not built yet; request kv_bits='fp16'")
+        self.kv_cache_config.mode = "fp16"
+        if self.compute_stream is None:
+            self.compute_stream = torch.cuda.Stream()
+            self.compute_stream_ptr = int(self.compute_stream.cuda_stream)
+        # fit mode with synthetic weights generates straight into HBM; everything else stages
+        # the packed layer records in pinned host memory first
+        self.stage_host = not (isinstance(self.model_metadata.source, SyntheticSource) and plan.mode == "fit")
+        self.policy = make_policy(plan.mode, self, plan.resident_windows)
+        self.policy.window_size = plan.window_size
+        self.policy.configure_policy_for_model(req)
+        self.input_pool = LayerAwareMemoryPool(total_memory_mb=int(self._compute_settings.input_pool_mb), placement="pinned")
+        self.output_pool = LayerAwareMemoryPool(total_memory_mb=int(self._compute_settings.output_pool_mb), placement="pinned")
+        settings = get_settings()
+        pages = int(settings.kv_cache.pool_pages) or max(1, (self.kv_cache_config.max_tokens + 63) // 64) * 8
+        self.model = get_ring_model(self.model_metadata.model_type, self.model_metadata.model_config,
+                                    assigned_layers=self.assigned_layers, is_api_layer=False,
+                                    kv_pool_pages=pages, wire_dtype=self._wire_dtype_str)
+        self.model.apply_quantization_from_config(self.model_metadata.model_config, model_metadata=self.model_metadata)
+        # embed / norm / head iff this shard owns layer 0 / the last layer (reference runtime.py:263-273)
+        has_start = 0 in self.assigned_layers
+        has_end = (self.model_metadata.num_layers - 1) in self.assigned_layers
+        tied = bool(self.model_metadata.model_config.get("tie_word_embeddings", False))
+        api: Dict[str, torch.Tensor] = {}
+
+        def _dev(info):
+            src = self.model_metadata.source
+            if isinstance(src, SyntheticSource):
+                t = torch.empty(tuple(info.shape), dtype=torch.bfloat16, device="cuda")
+                src.fill_device(info, t)
+                return t
+            return load_weight(info, {}, src).to("cuda", non_blocking=False).contiguous()
+
+        if has_start or (has_end and tied):
+            api["embed_tokens.weight"] = _dev(self.model_metadata.embed_tokens["weight"])
+        if has_end:
+            api["norm.weight"] = _dev(self.model_metadata.norm["weight"])
+            if not tied:
+                w = _dev(self.model_metadata.lm_head["weight"])
+                if w.shape[0] != self.model.vocab_size and w.shape[1] == self.model.vocab_size:
+                    w = w.t().contiguous()  # transposed (hidden, vocab) head accepted (utils/model.py:341-346)
+                api["lm_head.weight"] = w
+        self._api_tensors = api
+        if api:
+            self.model.load_weights(list(api.items()), strict=False)
+
+    def unload_model_core(self) -> ShardUnloadModelResponse:
+        try:
+            with self._model_lock:
+                if self.model is None:
+                    return ShardUnloadModelResponse(success=True, message="No model loaded")
+                while not self.activation_recv_queue.empty():
+                    try:
+                        self.activation_recv_queue.get_nowait()
+                    except queue.Empty:
+                        break
+                if self.compute_stream is not None:
+                    self.compute_stream.synchronize()
+                for ns in self._kv_by_nonce.values():
+                    ns.free()
+                self._kv_by_nonce.clear()
+                self._kv_last_seen.clear()
+                self.policy.clear()
+                self.policy = NoopPolicy(runtime=self, resident_windows=1)
+                self.model.destroy()
+                self.model = None
+                self.cache = None
+                self.model_metadata = None
+                self.assigned_layers = []
+                self.model_path = None
+                self._assigned_sorted = []
+                self._assigned_set = set()
+                self.input_pool = None
+                self.output_pool = None
+                self._api_tensors = {}
+                gc.collect()
+                torch.cuda.empty_cache()
+            return ShardUnloadModelResponse(success=True, message="Model unloaded successfully")
+        except Exception as e:
+            logger.exception("Node %s: Error unloading model: %s", self.shard_id, e)
+            return ShardUnloadModelResponse(success=False, message=f"Error unloading model: {str(e)}")
+
+    def reset_cache(self):
+        if not self.model:
+            logger.warning("Node %s: Cannot reset cache - no model loaded", self.shard_id)
+            return
+        self.cache = None
+
+    def compute(self, activation_msg: ActivationMessage) -> None:
+        if not self.policy:
+            logger.error("Runtime %s: no compute policy configured", self.shard_id)
+            return
+        self.policy.process(activation_msg)
+
+    def _compute_worker(self) -> None:
+        if torch.cuda.is_available():
+            torch.cuda.set_device(torch.cuda.current_device())
+        while self.running:
+            try:
+                activation_msg = self.activation_recv_queue.get(timeout=1.0)
+                self.compute(activation_msg)
+            except queue.Empty:
+                continue
+            except Exception as e:
+                logger.error("Compute worker error: %s", e)
+
+    def get_or_make_kv(self, nonce: str) -> NonceState:
+        """Per-nonce KV for this shard's local layers, with the reference's TTL sweep
+        (runtime.py:374-396)."""
+        if not self.model:
+            raise RuntimeError("Model not initialized")
+        now = time.perf_counter()
+        ttl = float(self._kv_ttl_s)
+        for n, ts in list(self._kv_last_seen.items()):
+            if (now - ts) > ttl and n != nonce:
+                self._kv_last_seen.pop(n, None)
+                old = self._kv_by_nonce.pop(n, None)
+                if old is not None:
+                    if self.compute_stream is not None:
+                        self.compute_stream.synchronize()
+                    old.free()
+        ns = self._kv_by_nonce.get(nonce)
+        if ns is None:
+            ns = NonceState(self.model, self.kv_cache_config.max_tokens)
+            self._kv_by_nonce[nonce] = ns
+        self._kv_last_seen[nonce] = time.perf_counter()
+        return ns
+
+    def start(self):
+        self.running = True
+        self.compute_thread = threading.Thread(target=self._compute_worker, daemon=True)
+        self.compute_thread.start()

@@ -1,0 +1,280 @@
+"""safetensors header parser + ModelMetadata (reference src/dnet/utils/model.py:27-155,388-467).
+
+Three weight sources share the ModelMetadata/TensorInfo contract:
+  * a local HF-style directory of *.safetensors + config.json (the reference path);
+  * ``HostDictSource``: an in-memory {name: tensor} checkpoint (parity tests feed the
+    oracle's synthetic weights through it);
+  * ``SyntheticSource``: shape-only random-init weights generated directly in HBM
+    (bench.py: there is no network for real checkpoints).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import mmap
+import re
+import struct
+from collections import defaultdict
+from dataclasses import dataclass
+from functools import cached_property
+from pathlib import Path
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+
+EMBED_TOKENS_RE = re.compile(r"^model\.embed_tokens\.(.+)$")
+LAYERS_RE = re.compile(r"^model\.layers\.(\d+)\.(.+)$")
+LM_HEAD_RE = re.compile(r"^lm_head\.(.+)$")
+NORM_RE = re.compile(r"^model\.norm\.(.+)$")
+
+
+def get_model_layer_name(layer_idx: int, name: str) -> str:
+    return f"layers.{layer_idx}.{name}"
+
+
+def get_model_embed_tokens_name(name: str) -> str:
+    return f"embed_tokens.{name}"
+
+
+def get_lm_head_name(name: str) -> str:
+    return f"lm_head.{name}"
+
+
+def get_model_norm_name(name: str) -> str:
+    return f"norm.{name}"
+
+
+@dataclass(slots=True, frozen=True)
+class TensorInfo:
+    """The tensor information stored inside safetensor file."""
+
+    dtype: str
+    shape: Tuple[int, ...]
+    size_bytes: int
+    offset: int
+    filename: str
+
+
+@dataclass(frozen=True)
+class ModelMetadata:
+    """LLM model metadata"""
+
+    path: Any
+    weight_info: Dict[int, Dict[str, TensorInfo]]
+    embed_tokens: Dict[str, TensorInfo]
+    lm_head: Dict[str, TensorInfo]
+    norm: Dict[str, TensorInfo]
+    config: Any
+    source: Any = None  # HostDictSource / SyntheticSource, None for files
+
+    @cached_property
+    def embedding_size(self) -> int:
+        embedding_size = self.model_config.get("embedding_size")
+        if embedding_size is None:
+            if self.embed_tokens and "weight" in self.embed_tokens:
+                embedding_size = self.embed_tokens["weight"].shape[1]
+            else:
+                embedding_size = self.model_config.get("hidden_size")
+        if embedding_size is None:
+            raise ValueError("Could not find embedding_size or hidden_size in model metadata")
+        return embedding_size
+
+    @cached_property
+    def num_layers(self) -> int:
+        try:
+            n = int(self.config.get("num_hidden_layers"))
+            if n > 0:
+                return n
+        except Exception:
+            pass
+        return max(self.weight_info.keys()) + 1
+
+    @cached_property
+    def model_type(self) -> str:
+        return self.config["model_type"]
+
+    @property
+    def model_config(self) -> Any:
+        return self.config
+
+
+def get_safetensor_details(path) -> Dict[str, TensorInfo]:
+    """8-byte LE header length + JSON header; offsets are absolute file offsets."""
+    with open(path, "rb") as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        header_len = struct.unpack("<Q", mm[:8])[0]
+        header = json.loads(mm[8:8 + header_len].decode("utf-8"))
+        data_base = 8 + header_len
+        details = {}
+        for name, info in header.items():
+            if name == "__metadata__":
+                continue
+            start, end = info["data_offsets"]
+            details[name] = TensorInfo(dtype=info["dtype"], shape=tuple(info["shape"]), size_bytes=end - start,
+                                       offset=data_base + start, filename=str(path))
+        mm.close()
+        return details
+
+
+def _classify(details: Dict[str, TensorInfo], weight_info, embed_tokens, lm_head, norm) -> None:
+    for key, val in details.items():
+        if m := EMBED_TOKENS_RE.match(key):
+            embed_tokens[m.group(1)] = val
+        elif m := LM_HEAD_RE.match(key):
+            lm_head[m.group(1)] = val
+        elif m := NORM_RE.match(key):
+            norm[m.group(1)] = val
+        elif m := LAYERS_RE.match(key):
+            layer_idx, suffix = m.groups()
+            weight_info[int(layer_idx)][suffix] = val
+        else:
+            raise RuntimeError(f"Unexpected key {key}")
+
+
+def _validate_layers(config, weight_info) -> None:
+    try:
+        cfg_layers = int(config.get("num_hidden_layers", -1))
+    except Exception:
+        cfg_layers = -1
+    if cfg_layers > 0:
+        bad = [i for i in weight_info if i < 0 or i >= cfg_layers]
+        if bad:
+            raise RuntimeError(
+                f"Layer indices out of range for model (num_hidden_layers={cfg_layers}): {sorted(set(bad))}")
+
+
+_ST_NAME = {torch.bfloat16: "BF16", torch.float16: "F16", torch.float32: "F32", torch.int32: "I32",
+            torch.int64: "I64", torch.uint8: "U8", torch.int8: "I8"}
+
+
+class HostDictSource:
+    """An in-memory checkpoint {HF name: host tensor}."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], config: dict):
+        self.tensors = tensors
+        self.config = config
+
+    def details(self) -> Dict[str, TensorInfo]:
+        return {k: TensorInfo(_ST_NAME[v.dtype], tuple(v.shape), v.numel() * v.element_size(), 0, f"mem://{k}")
+                for k, v in self.tensors.items()}
+
+    def host_tensor(self, info: TensorInfo) -> torch.Tensor:
+        return self.tensors[info.filename[len("mem://"):]]
+
+
+class SyntheticSource:
+    """Random-init weights of a given architecture, generated on the device.
+
+    normal(0, std) from a per-tensor seeded torch.cuda generator; norm weights are 1.
+    ``host_tensor`` is unavailable: tensors are materialised straight into HBM slots.
+    """
+
+    def __init__(self, config: dict, seed: int = 0, std: float = 0.02, layers=None):
+        self.config = config
+        self.seed = seed
+        self.std = std
+        c = config
+        H, F_, V = c["hidden_size"], c["intermediate_size"], c["vocab_size"]
+        hd = c.get("head_dim") or H // c["num_attention_heads"]
+        qd, kd = c["num_attention_heads"] * hd, c.get("num_key_value_heads", c["num_attention_heads"]) * hd
+        self._shapes: Dict[str, Tuple[int, ...]] = {}
+        for l in (range(c["num_hidden_layers"]) if layers is None else layers):
+            p = f"model.layers.{l}."
+            self._shapes[p + "self_attn.q_proj.weight"] = (qd, H)
+            self._shapes[p + "self_attn.k_proj.weight"] = (kd, H)
+            self._shapes[p + "self_attn.v_proj.weight"] = (kd, H)
+            self._shapes[p + "self_attn.o_proj.weight"] = (H, qd)
+            self._shapes[p + "mlp.gate_proj.weight"] = (F_, H)
+            self._shapes[p + "mlp.up_proj.weight"] = (F_, H)
+            self._shapes[p + "mlp.down_proj.weight"] = (H, F_)
+            self._shapes[p + "input_layernorm.weight"] = (H,)
+            self._shapes[p + "post_attention_layernorm.weight"] = (H,)
+        self._shapes["model.embed_tokens.weight"] = (V, H)
+        self._shapes["model.norm.weight"] = (H,)
+        if not c.get("tie_word_embeddings", False):
+            self._shapes["lm_head.weight"] = (V, H)
+        self._names = list(self._shapes)
+
+    def details(self) -> Dict[str, TensorInfo]:
+        out = {}
+        for k, shp in self._shapes.items():
+            n = 1
+            for s in shp:
+                n *= s
+            out[k] = TensorInfo("BF16", shp, n * 2, 0, f"syn://{k}")
+        return out
+
+    def fill_device(self, info: TensorInfo, dst: torch.Tensor) -> None:
+        """Generate the tensor directly into ``dst`` (a bf16 cuda view of the right shape)."""
+        name = info.filename[len("syn://"):]
+        if name.endswith("layernorm.weight") or name == "model.norm.weight":
+            dst.fill_(1.0)
+            return
+        g = torch.Generator(device=dst.device)
+        g.manual_seed(self.seed * 1000003 + self._names.index(name))
+        std = 1.0 if name == "model.embed_tokens.weight" else self.std
+        # generate in fp32 chunks to bound temporary memory
+        flat = dst.view(-1)
+        step = 1 << 26
+        for i in range(0, flat.numel(), step):
+            n = min(step, flat.numel() - i)
+            flat[i:i + n] = (torch.randn(n, generator=g, device=dst.device, dtype=torch.float32) * std).to(dst.dtype)
+
+    def host_tensor(self, info: TensorInfo) -> torch.Tensor:
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        t = torch.empty(info.shape, dtype=torch.bfloat16, device=dev)
+        self.fill_device(info, t)
+        return t.cpu()
+
+
+def get_model_metadata(model_path) -> ModelMetadata:
+    """Accepts a local directory (reference behaviour, minus the HF download), a
+    HostDictSource or a SyntheticSource."""
+    weight_info: Dict[int, Dict[str, Any]] = defaultdict(dict)
+    embed_tokens, lm_head, norm = {}, {}, {}
+    if isinstance(model_path, (HostDictSource, SyntheticSource)):
+        src = model_path
+        _classify(src.details(), weight_info, embed_tokens, lm_head, norm)
+        _validate_layers(src.config, weight_info)
+        return ModelMetadata(Path("."), dict(weight_info), embed_tokens, lm_head, norm, src.config, src)
+    path = Path(model_path)
+    if not (path.exists() and path.is_dir()):
+        raise FileNotFoundError(f"model path {model_path!r} is not a local directory (no network: HF download unsupported)")
+    with open(path / "config.json", "r") as f:
+        config = json.load(f)
+    for weight in sorted(glob.glob(str(path / "*.safetensors"))):
+        _classify(get_safetensor_details(weight), weight_info, embed_tokens, lm_head, norm)
+    _validate_layers(config, weight_info)
+    return ModelMetadata(path, dict(weight_info), embed_tokens, lm_head, norm, config)
+
+
+class MappedFile:
+    """Read-only mmap of a weight file (reference utils/model.py:215-239)."""
+
+    def __init__(self, file_path: str):
+        self.file_path = file_path
+        self.file = open(file_path, "rb")
+        self.mmap = mmap.mmap(self.file.fileno(), 0, access=mmap.ACCESS_READ)
+
+    def close(self):
+        try:
+            self.mmap.close()
+        finally:
+            self.file.close()
+
+
+def load_weight(wt: TensorInfo, mapped_files: Dict[str, MappedFile], source=None) -> torch.Tensor:
+    """Byte-exact host tensor for one checkpoint entry (reference utils/model.py:242-260).
+    BF16 stays BF16 bit-for-bit (the reference round-trips uint16<<16 -> fp32 -> bf16,
+    which is the identity on the bit pattern)."""
+    from .serialization import safetensor_torch_dtype
+
+    if wt.filename.startswith(("mem://", "syn://")):
+        if source is None:
+            raise ValueError("in-memory tensor needs its source")
+        return source.host_tensor(wt)
+    if wt.filename not in mapped_files:
+        mapped_files[wt.filename] = MappedFile(wt.filename)
+    mv = memoryview(mapped_files[wt.filename].mmap)[wt.offset:wt.offset + wt.size_bytes]
+    td = safetensor_torch_dtype[wt.dtype]
+    return torch.frombuffer(mv, dtype=torch.uint8).view(td).reshape(tuple(wt.shape))

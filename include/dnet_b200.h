@@ -1,0 +1,186 @@
+/*
+ * dnet_b200.h -- C ABI of libdnet_b200.so: the B200-native shard forward of dnet's
+ * pipelined ring (per-layer decode forward, end-shard sampling, ring hop, layer swap).
+ *
+ * The reference (firstbatchxyz/dnet @ e76f54a) has no C/FFI seam on this path: its
+ * seams are Python plug-in points (ComputePolicy registry, BaseRingModel operator
+ * API).  Every entry point below is what a binding for those seams would call; the
+ * reference interface each one replaces is cited as file:line relative to
+ * /root/reference/.  INTEGRATION.md shows the reference-side ctypes stub.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw device pointers, sizes; no torch / C++ types.
+ *   - every function returns 0 on success or a negative DN_E* code and never throws;
+ *     dn_last_error() returns a thread-local human-readable message.
+ *   - the caller owns every buffer and stream it passes in.  Functions taking a
+ *     stream are asynchronous with respect to it and contain no hidden host sync.
+ *   - one compute thread per shard, as in the reference (shard/runtime.py:364-372);
+ *     handles are thread-compatible, not thread-safe.
+ *   - activations are row-major [T, hidden] bf16 (the reference's (1,T,H) array with
+ *     the unit batch dim dropped); weights are HF/MLX layout [out, in] row-major bf16,
+ *     y = x W^T.
+ */
+#ifndef DNET_B200_H
+#define DNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_OK 0
+#define DN_EINVAL (-22)   /* bad argument / unsupported shape */
+#define DN_ENOMEM (-12)   /* device / pinned allocation failed */
+#define DN_ENOENT (-2)    /* layer not hosted / not bound */
+#define DN_ECUDA (-5)     /* a CUDA runtime call failed; see dn_last_error() */
+#define DN_ETIME (-62)    /* hop wait timed out */
+#define DN_ENOSPC (-28)   /* KV capacity exceeded */
+
+#define DN_DTYPE_BF16 0
+
+/* index of each tensor in the dev_ptrs array handed to dn_bind_layer
+ * (reference utils/model.py:27-43 key regexes) */
+enum {
+  DN_W_Q = 0, DN_W_K, DN_W_V, DN_W_O, DN_W_GATE, DN_W_UP, DN_W_DOWN,
+  DN_W_LN1, DN_W_LN2,
+  DN_W_QB, DN_W_KB, DN_W_VB,   /* optional q/k/v bias (qwen2); NULL for llama */
+  DN_W_COUNT
+};
+
+typedef struct dn_model dn_model;   /* one shard's model slice + scratch */
+typedef struct dn_kv dn_kv;         /* one nonce's paged KV + step state  */
+typedef struct dn_graph dn_graph;   /* an instantiated CUDA graph         */
+typedef void* dn_stream;            /* cudaStream_t                       */
+typedef void* dn_event;             /* cudaEvent_t                        */
+
+/* mlx_lm.models.llama.ModelArgs as consumed by reference core/models/llama.py:33 */
+typedef struct dn_model_cfg {
+  int32_t hidden;          /* hidden_size */
+  int32_t n_heads;         /* num_attention_heads */
+  int32_t n_kv_heads;      /* num_key_value_heads */
+  int32_t head_dim;        /* must be 128 */
+  int32_t ffn;             /* intermediate_size */
+  int32_t vocab;           /* vocab_size */
+  int32_t n_layers_total;  /* num_hidden_layers of the whole model */
+  float rms_eps;           /* rms_norm_eps */
+  int32_t tie_embeddings;  /* lm_head = embed_tokens (core/models/llama.py:62-66) */
+  int32_t dtype;           /* DN_DTYPE_BF16 */
+  int32_t wire_dtype;      /* must equal dtype (mixed wire dtype) */
+  int32_t kv_page_tokens;  /* 64 */
+  int32_t kv_pool_pages;   /* pages in the shard's KV pool (shared by all nonces) */
+} dn_model_cfg;
+
+/* ---- process / device -------------------------------------------------- */
+int dn_init(int device);                         /* cudaSetDevice + capability check (sm_100) */
+const char* dn_last_error(void);
+const char* dn_version(void);
+int dn_set_option(const char* key, int64_t value); /* "pdl" (0/1), "l2_prefetch_kb" */
+int64_t dn_launch_count(void);                   /* kernels launched by this library so far
+                                                    (graph replays count their nodes) */
+int dn_device_sm_count(void);
+
+/* ---- model slice: replaces BaseRingModel ctor + load_weights / unload_layers
+ *      (reference core/models/llama.py:20-54, core/models/base.py:111-195,474-486).
+ *      The model BORROWS weight memory (owned by the caller's WeightCache). */
+int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layers, int n_layers,
+                    const float* inv_freq_host /* head_dim/2 fp32 */, dn_model** out);
+int dn_model_destroy(dn_model* m);
+int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_ptrs /* DN_W_COUNT */);
+int dn_unbind_layer(dn_model* m, int abs_layer);
+int dn_layer_is_bound(dn_model* m, int abs_layer);
+/* embed_tokens / final norm / lm_head (reference shard/runtime.py:263-273); any may be NULL */
+int dn_bind_api(dn_model* m, const void* embed, const void* norm, const void* head);
+int dn_model_max_chunk(dn_model* m);             /* largest T accepted by dn_layer_forward */
+
+/* ---- per-nonce KV: replaces make_cache + mlx_lm KVCache
+ *      (reference utils/model.py:470-555, shard/runtime.py:374-396) */
+int dn_kv_create(dn_model* m, int max_tokens, dn_kv** out);
+int dn_kv_free(dn_kv* kv);
+int dn_kv_reset(dn_kv* kv, dn_stream s);          /* offset <- 0 */
+int dn_kv_offset(dn_kv* kv);                      /* host mirror of cache.offset */
+int dn_kv_advance(dn_kv* kv, int T, dn_stream s); /* offset += T (device + host mirror) */
+int dn_kv_seek(dn_kv* kv, int pos, dn_stream s);  /* offset <- pos (chunked prefill across windows) */
+int dn_kv_set_token(dn_kv* kv, int32_t token, dn_stream s); /* device step-state token */
+int dn_kv_note_advance(dn_kv* kv, int T);          /* host mirror only: a graph replay advanced the offset */
+void* dn_kv_token_ptr(dn_kv* kv);                 /* device int32*: step-state token */
+
+/* ---- operators (BaseRingModel API, reference core/models/base.py:20-73) ---- */
+/* embed: core/models/llama.py:56-57.  ids: device int32[T]. x_out: [T,hidden] bf16 */
+int dn_embed(dn_model* m, const int32_t* ids_dev, int T, void* x_out, dn_stream s);
+/* apply_single_layer + the policy's cast to wire dtype
+ * (core/models/llama.py:76-102, shard/policies/fit_in_memory.py:102-109).
+ * x_inout [T,hidden] bf16, updated in place.  KV positions are kv.offset..+T-1;
+ * the caller advances the offset once per message with dn_kv_advance. */
+int dn_layer_forward(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s);
+/* the window loop of FitInMemoryPolicy.process (fit_in_memory.py:78-124) in one call */
+int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, int T,
+                      dn_kv* kv, dn_stream s);
+/* measurement hooks for bench.py: per-kernel device times (CUDA events on stream s between
+ * the five launches of one layer: qkv+rope+append, attention, o_proj, gate/up, down) */
+int dn_layer_forward_timed(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s,
+                           float ms_out[5]);
+int dn_head_timed(dn_model* m, const void* x, int T, dn_stream s, float* ms_out);
+/* normalize + lm_project on the LAST position + Sampler.sample with temperature==0
+ * (fit_in_memory.py:134-157, core/decoding/sampler.py:15-65).  token_out / logprob_out:
+ * device-accessible (device or mapped pinned) int32 / float.  If kv != NULL the token
+ * is also written to the nonce's step state (feeds the next dn_embed). */
+int dn_head_sample_greedy(dn_model* m, const void* x, int T, dn_kv* kv, int32_t* token_out,
+                          float* logprob_out, dn_stream s);
+/* fp32 last-position logits BEFORE the bf16 rounding (parity / stochastic sampling) and
+ * the bf16-rounded logits the reference's Linear returns; either pointer may be NULL */
+int dn_head_logits(dn_model* m, const void* x, int T, float* logits_f32_out,
+                   void* logits_bf16_out, dn_stream s);
+
+/* ---- CUDA graph capture of a window / step (replaces the per-layer Python loop +
+ *      mx.eval per window, fit_in_memory.py:102-113) */
+int dn_graph_begin(dn_stream s);
+int dn_graph_end(dn_stream s, dn_graph** out);
+int dn_graph_launch(dn_graph* g, dn_stream s);
+int dn_graph_destroy(dn_graph* g);
+int dn_graph_num_nodes(dn_graph* g);
+
+/* ---- ring hop data plane: replaces RingAdapter._send_activation + gRPC
+ *      StreamActivations for the tensor bytes (reference shard/adapters/ring.py:265-299,
+ *      shard/grpc_servicer/servicer.py:129-161).  Slots live on the RECEIVING GPU. */
+int dn_hop_alloc(size_t bytes, void** dev_ptr);             /* cudaMalloc, IPC-exportable, zeroed */
+int dn_hop_free(void* dev_ptr);
+int dn_hop_export(void* dev_ptr, uint8_t handle_out[64]);   /* cudaIpcGetMemHandle */
+int dn_hop_import(const uint8_t handle[64], void** dev_ptr);/* cudaIpcOpenMemHandle */
+int dn_hop_close(void* imported_ptr);
+int dn_enable_peer(int peer_device);                        /* same-process multi-GPU */
+/* copy bytes into the peer slot on stream s, then publish seq to *dst_flag (system scope) */
+int dn_hop_send(void* dst_slot, const void* src, size_t bytes, uint32_t* dst_flag, uint32_t seq,
+                dn_stream s);
+/* make stream s wait until *flag >= seq (device-side spin, bounded by timeout_ms; on timeout
+ * the kernel sets *err_flag (device uint32, may be NULL) and returns so the GPU never hangs) */
+int dn_hop_wait(const uint32_t* flag, uint32_t seq, uint32_t timeout_ms, uint32_t* err_flag,
+                dn_stream s);
+
+/* ---- layer swap: replaces LayerManager.load_layer_to_gpu / WeightCache materialise
+ *      (reference utils/layer_manager.py:229-282, core/memory/weight_cache.py:68-196) */
+int dn_pinned_alloc(size_t bytes, void** host_ptr);         /* cudaHostAlloc (portable) */
+int dn_pinned_free(void* host_ptr);
+int dn_device_alloc(size_t bytes, void** dev_ptr);
+int dn_device_free(void* dev_ptr);
+/* stage one layer slot from pinned host memory on the prefetch stream; record done */
+int dn_slot_prefetch(void* dst_dev, const void* src_pinned, size_t bytes, dn_stream prefetch,
+                     dn_event done);
+int dn_stream_create(dn_stream* out, int high_priority);
+int dn_stream_destroy(dn_stream s);
+int dn_stream_sync(dn_stream s);
+int dn_stream_wait_event(dn_stream s, dn_event e);
+int dn_event_create(dn_event* out, int timing);
+int dn_event_destroy(dn_event e);
+int dn_event_record(dn_event e, dn_stream s);
+int dn_event_query(dn_event e);                              /* 1 done, 0 pending, <0 error */
+int dn_event_sync(dn_event e);
+int dn_event_elapsed_ms(dn_event a, dn_event b, float* ms);
+int dn_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, dn_stream s);
+int dn_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, dn_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNET_B200_H */
