@@ -110,13 +110,7 @@ static size_t gemv_smem(int T, int K) { return (size_t)T * K * 2 + (2 * NW * 32 
 
 template <int T, class Op>
 static cudaError_t launch_gemv(const Op& op, int units, cudaStream_t s) {
-  static bool attr_done = false;  // per instantiation
   const size_t smem = gemv_smem(T, op.K);
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemv<T, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
   int grid = CTAS_PER_SM * g_sms;
   if (grid > units) grid = units;
   if (grid < 1) grid = 1;
@@ -150,6 +144,22 @@ static cudaError_t launch_attn(dn_model* m, const bf16* q, const bf16* pool, con
 // ---------------------------------------------------------------------------------
 // process / device
 // ---------------------------------------------------------------------------------
+template <int T, class Op>
+static cudaError_t set_gemv_attr() {
+  return cudaFuncSetAttribute(k_gemv<T, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+// every instantiation gets its dynamic-smem limit at init, never inside a graph capture
+static cudaError_t init_kernel_attrs() {
+  cudaError_t e;
+#define SETA(T, Op) if ((e = set_gemv_attr<T, Op>()) != cudaSuccess) return e;
+  SETA(1, OpQKV) SETA(2, OpQKV) SETA(4, OpQKV)
+  SETA(1, OpOProj) SETA(2, OpOProj) SETA(4, OpOProj)
+  SETA(1, OpGateUp) SETA(2, OpGateUp) SETA(4, OpGateUp)
+  SETA(1, OpHead)
+#undef SETA
+  return cudaSuccess;
+}
+
 extern "C" const char* dn_last_error(void) { return g_err; }
 extern "C" const char* dn_version(void) { return "dnet_b200 0.1 (sm_100a)"; }
 extern "C" int64_t dn_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -167,6 +177,7 @@ extern "C" int dn_init(int device) {
   if (p.major != 10) return fail(DN_EINVAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
   g_sms = p.multiProcessorCount;
   g_device = device;
+  CK(init_kernel_attrs());
   return DN_OK;
 }
 

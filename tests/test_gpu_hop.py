@@ -1,0 +1,62 @@
+"""-m gpu: the ring-hop data plane and layer-swap plumbing of the C ABI on one device."""
+import ctypes as C
+
+import pytest
+import torch
+
+from dnet_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hop_send_wait_and_bounded_timeout(cuda_lib):
+    lib = cuda_lib
+    slot, flags = C.c_void_p(), C.c_void_p()
+    _cabi.check(lib.dn_hop_alloc(8192, C.byref(slot)))
+    _cabi.check(lib.dn_hop_alloc(64, C.byref(flags)))
+    s_tx, s_rx = torch.cuda.Stream(), torch.cuda.Stream()
+    src = torch.arange(4096, dtype=torch.int16, device="cuda")
+    dst_view = torch.empty(4096, dtype=torch.int16).pin_memory()
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    # receiver first: waits on seq 1, then copies the slot out
+    _cabi.check(lib.dn_hop_wait(flags.value, 1, 2000, err.data_ptr(), s_rx.cuda_stream))
+    _cabi.check(lib.dn_memcpy_d2h(dst_view.data_ptr(), slot.value, 8192, s_rx.cuda_stream))
+    _cabi.check(lib.dn_hop_send(slot.value, src.data_ptr(), 8192, flags.value, 1, s_tx.cuda_stream))
+    s_rx.synchronize()
+    assert torch.equal(dst_view, src.cpu()) and int(err.item()) == 0
+    # a flag that never arrives: the wait kernel gives up after the timeout and reports it
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(s_rx)
+    _cabi.check(lib.dn_hop_wait(flags.value, 99, 30, err.data_ptr(), s_rx.cuda_stream))
+    t1.record(s_rx)
+    s_rx.synchronize()
+    assert int(err.item()) == 1 and 20 <= t0.elapsed_time(t1) < 500
+    h = (C.c_uint8 * 64)()
+    _cabi.check(lib.dn_hop_export(slot.value, h))
+    assert any(h)
+    _cabi.check(lib.dn_hop_free(slot.value))
+    _cabi.check(lib.dn_hop_free(flags.value))
+
+
+def test_slot_prefetch_pinned_to_hbm_with_event(cuda_lib):
+    lib = cuda_lib
+    host, dev, ev, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = 1 << 20
+    _cabi.check(lib.dn_pinned_alloc(n, C.byref(host)))
+    _cabi.check(lib.dn_device_alloc(n, C.byref(dev)))
+    _cabi.check(lib.dn_event_create(C.byref(ev), 0))
+    _cabi.check(lib.dn_stream_create(C.byref(st), 0))
+    C.memset(host.value, 0x5A, n)
+    _cabi.check(lib.dn_slot_prefetch(dev.value, host.value, n, st.value, ev.value))
+    _cabi.check(lib.dn_event_sync(ev.value))
+    assert lib.dn_event_query(ev.value) == 1
+    back = torch.empty(n, dtype=torch.uint8).pin_memory()
+    _cabi.check(lib.dn_memcpy_d2h(back.data_ptr(), dev.value, n, st.value))
+    _cabi.check(lib.dn_stream_sync(st.value))
+    assert int(back.min()) == 0x5A and int(back.max()) == 0x5A
+    for f, p in ((lib.dn_event_destroy, ev), (lib.dn_stream_destroy, st), (lib.dn_device_free, dev), (lib.dn_pinned_free, host)):
+        _cabi.check(f(p.value))
+
+
+def test_launch_counter_counts_graph_nodes(cuda_lib):
+    assert cuda_lib.dn_launch_count() >= 0 and cuda_lib.dn_device_sm_count() >= 100

@@ -1,0 +1,347 @@
+"""-m gpu: the CUDA path (through the reference-facing policy / model API, which calls
+libdnet_b200.so through the C ABI) against the CPU oracle, the committed golden fixtures
+and size-independent properties.  Tolerance for floating point: max|a-b|/max|b| <= 1e-3
+on fp32 logits (north_star); greedy token ids bit-exact."""
+import ctypes as C
+import queue
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import (load_golden, make_runtime, oracle_weights, rel_inf, ring_generate, token_message)
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3
+
+
+def _bf16(a_int16: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(a_int16.copy()).view(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def tiny(cuda_lib):
+    g = load_golden("tiny_llama")
+    return g, oracle_weights(g["config"], g["wseed"])
+
+
+@pytest.fixture(scope="module")
+def tiny_b(cuda_lib):
+    g = load_golden("tiny_qwen2_tied")
+    return g, oracle_weights(g["config"], g["wseed"])
+
+
+def _last_logits(rt, nonce):
+    ns = rt._kv_by_nonce[nonce]
+    x = ns.x1 if ns._x is None else None
+    return ns
+
+
+def test_per_layer_hidden_states_and_logits_vs_golden(tiny):
+    """C-ABI operators one layer at a time (BaseRingModel.apply_single_layer), prompt of 7
+    tokens = chunks of 4+2+1 through the T-templated kernels."""
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]), cuda_graphs=False)
+    try:
+        m = rt.model
+        ns = rt.get_or_make_kv("probe")
+        # bind all layers through the policy's own path
+        pol = rt.policy
+        msg = token_message(rt, "probe", g["prompt"].tolist())
+        to_bind = pol._bind_layer_weights(list(range(cfgd["num_hidden_layers"])), msg)
+        m.load_weights(list(to_bind.items()))
+        ids = torch.tensor(g["prompt"], dtype=torch.int32, device="cuda")
+        x = m.embed(ids[None])
+        emb = torch.stack([w["model.embed_tokens.weight"][int(i)] for i in g["prompt"]]).cuda()
+        assert torch.equal(x[0], emb)
+        worst = 0.0
+        for l in range(cfgd["num_hidden_layers"]):
+            x = m.apply_single_layer(l, x, ns.kv)
+            torch.cuda.synchronize()
+            got = x[0, -1].float().cpu()
+            ref = _bf16(g["hidden_prefill"][l]).float()
+            r = rel_inf(got, ref)
+            worst = max(worst, r)
+            mism = float((got != ref).float().mean())
+            assert r < 2e-2 and mism < 0.05, f"layer {l}: rel {r}, mismatching bf16 elements {mism}"
+        ns.kv.advance(len(g["prompt"]))
+        f32, b16 = m.head_logits(x[0])
+        torch.cuda.synchronize()
+        r = rel_inf(f32.cpu(), torch.from_numpy(g["logits_f32"][0]))
+        assert r <= LOGIT_TOL, f"logits rel err {r}"
+        assert torch.equal(b16.float().cpu(), f32.cpu().to(torch.bfloat16).float())
+        assert int(torch.argmax(b16.float())) == int(g["tokens"][0])
+    finally:
+        rt.unload_model_core()
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_greedy_generation_matches_golden_single_shard(tiny, graphs):
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]), cuda_graphs=graphs)
+    try:
+        out = ring_generate([rt], "n0", g["prompt"].tolist(), g["steps"])
+        assert [t for t, _, _ in out] == g["tokens"].tolist()          # bit-exact argmax ids
+        lp = np.array([p for _, p, _ in out], np.float32)
+        assert np.allclose(lp, g["logprobs"], rtol=2 ** -6, atol=2 ** -6)
+        assert rt._kv_by_nonce["n0"].kv.offset == len(g["prompt"]) + g["steps"] - 1
+    finally:
+        rt.unload_model_core()
+
+
+def test_every_step_logits_within_tolerance(tiny):
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]))
+    try:
+        ids = g["prompt"].tolist()
+        worst = 0.0
+        for step in range(g["steps"]):
+            msg = token_message(rt, "n1", ids)
+            rt.policy.process(msg)
+            res = rt.activation_send_queue.get_nowait()
+            ns = rt._kv_by_nonce["n1"]
+            x = ns.x_view(len(ids))
+            f32, _ = rt.model.head_logits(x)
+            torch.cuda.synchronize()
+            r = rel_inf(f32.cpu(), torch.from_numpy(g["logits_f32"][step]))
+            worst = max(worst, r)
+            assert res.token_id == int(g["tokens"][step])
+            ids = [res.token_id]
+        assert worst <= LOGIT_TOL, f"worst logits rel err {worst}"
+    finally:
+        rt.unload_model_core()
+
+
+@pytest.mark.parametrize("via_bytes", [False, True])
+def test_two_shards_bit_identical_to_one(tiny, via_bytes):
+    """device hand-off (NVLink hop path) and wire bytes (gRPC path) both reproduce the
+    single-shard result bit for bit: the split is pure data movement."""
+    g, w = tiny
+    cfgd = g["config"]
+    a = make_runtime(cfgd, w, [0, 1], shard_id="a")
+    b = make_runtime(cfgd, w, [2, 3], shard_id="b")
+    try:
+        out = ring_generate([a, b], "n0", g["prompt"].tolist(), g["steps"], via_bytes=via_bytes)
+        assert [t for t, _, _ in out] == g["tokens"].tolist()
+        assert a.activation_send_queue.empty() and b.activation_send_queue.empty()
+    finally:
+        a.unload_model_core()
+        b.unload_model_core()
+
+
+def test_multi_round_assignment_k2(tiny):
+    """k=2 rounds: shard a owns [[0],[2]], shard b owns [[1],[3]] -> four hops per token
+    (reference api/utils.py:62-131 round-robin blocks; the policy stops at the first
+    non-local layer, fit_in_memory.py:83-84)."""
+    g, w = tiny
+    cfgd = g["config"]
+    a = make_runtime(cfgd, w, [0, 2], shard_id="a")
+    b = make_runtime(cfgd, w, [1, 3], shard_id="b")
+    try:
+        ids = g["prompt"].tolist()
+        toks = []
+        for _ in range(5):
+            msg = token_message(a, "n0", ids)
+            for rt in (a, b, a, b):
+                rt.policy.process(msg)
+                msg = rt.activation_send_queue.get_nowait()
+            assert msg.is_final
+            toks.append(msg.token_id)
+            ids = [msg.token_id]
+        assert toks == g["tokens"][:5].tolist()
+    finally:
+        a.unload_model_core()
+        b.unload_model_core()
+
+
+def test_offload_and_sliding_fit_match_fit_bit_for_bit(tiny):
+    """layer swap (pinned host -> HBM slots on the prefetch stream) must not change a bit."""
+    g, w = tiny
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+    for win, res, mode in ((2, 2, "offload"), (2, 1, "sliding_fit"), (1, 1, "offload"), (3, 3, "offload")):
+        rt = make_runtime(cfgd, w, range(L), window_size=win, residency_size=res)
+        try:
+            assert rt.policy._mode == mode
+            assert rt.policy.weight_cache.max_weights <= max(win, 1) * max(1, rt.policy._resident_windows)
+            out = ring_generate([rt], "n0", g["prompt"].tolist(), 8)
+            assert [t for t, _, _ in out] == g["tokens"][:8].tolist(), (win, res, mode)
+            assert len(rt.policy.weight_cache.cache) <= rt.policy.weight_cache.max_weights + 1
+        finally:
+            rt.unload_model_core()
+
+
+def test_determinism_graph_vs_eager_and_pdl(tiny, cuda_lib):
+    g, w = tiny
+    cfgd = g["config"]
+    results = []
+    for graphs, pdl in ((True, 1), (False, 1), (True, 0), (False, 0), (True, 1)):
+        rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]), cuda_graphs=graphs)
+        cuda_lib.dn_set_option(b"pdl", pdl)
+        try:
+            out = ring_generate([rt], "n0", g["prompt"].tolist(), 10)
+            ns = rt._kv_by_nonce["n0"]
+            f32, _ = rt.model.head_logits(ns.x1)
+            torch.cuda.synchronize()
+            results.append(([t for t, _, _ in out], [p for _, p, _ in out], f32.cpu()))
+        finally:
+            rt.unload_model_core()
+    cuda_lib.dn_set_option(b"pdl", 1)
+    for r in results[1:]:
+        assert r[0] == results[0][0] and r[1] == results[0][1]
+        assert torch.equal(r[2], results[0][2])        # bitwise: fixed-order reductions
+
+
+def test_prefill_chunking_is_consistent_with_token_by_token(tiny):
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]))
+    try:
+        prompt = g["prompt"].tolist()
+        rt.policy.process(token_message(rt, "whole", prompt))
+        rt.activation_send_queue.get_nowait()
+        fa, _ = rt.model.head_logits(rt._kv_by_nonce["whole"].x_view(len(prompt)))
+        for t in prompt:
+            rt.policy.process(token_message(rt, "single", [t]))
+            last = rt.activation_send_queue.get_nowait()
+        fb, _ = rt.model.head_logits(rt._kv_by_nonce["single"].x1)
+        torch.cuda.synchronize()
+        assert rel_inf(fa.cpu(), fb.cpu()) <= LOGIT_TOL
+        assert last.token_id == int(g["tokens"][0])
+    finally:
+        rt.unload_model_core()
+
+
+def test_qwen2_bias_tied_head_rope_scaling_page_boundary(tiny_b):
+    """GQA group 4, q/k/v bias, tied embeddings, llama3 rope scaling, 70-token prompt:
+    crosses the 64-token KV page boundary during prefill and decode."""
+    g, w = tiny_b
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]))
+    try:
+        ids = g["prompt"].tolist()
+        worst = 0.0
+        for step in range(g["steps"]):
+            rt.policy.process(token_message(rt, "q", ids))
+            res = rt.activation_send_queue.get_nowait()
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce["q"].x_view(len(ids)))
+            torch.cuda.synchronize()
+            worst = max(worst, rel_inf(f32.cpu(), torch.from_numpy(g["logits_f32"][step])))
+            assert res.token_id == int(g["tokens"][step])
+            ids = [res.token_id]
+        assert worst <= LOGIT_TOL, worst
+    finally:
+        rt.unload_model_core()
+
+
+def test_top_logprobs_and_stochastic_sampling_path(tiny):
+    from oracle.llama_oracle import sample_greedy
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]))
+    try:
+        rt.policy.process(token_message(rt, "t", g["prompt"].tolist(), req_logprobs=True, req_top_logprobs=5))
+        res = rt.activation_send_queue.get_nowait()
+        ref = sample_greedy(_bf16(g["logits_bf16"][0]), True, 5)
+        assert res.token_id == ref.token_id and len(res.top_logprobs) == 5
+        assert list(res.top_logprobs)[0] == ref.token_id
+        assert set(res.top_logprobs) == set(ref.top_logprobs)
+        # temperature > 0: sampled id is a valid index and top_k=1 degenerates to argmax
+        rt.policy.process(token_message(rt, "s", g["prompt"].tolist(), temperature=0.7, top_k=1))
+        res2 = rt.activation_send_queue.get_nowait()
+        assert res2.token_id == int(g["tokens"][0])
+    finally:
+        rt.unload_model_core()
+
+
+def test_error_behaviour_matches_policy_contract(tiny):
+    """never raises; releases the input buffer; emits nothing on failure."""
+    from dnet_b200 import _cabi
+    g, w = tiny
+    cfgd = g["config"]
+    rt = make_runtime(cfgd, w, [0, 1], max_tokens=64)
+    try:
+        msg = token_message(rt, "x", list(range(70)))            # exceeds the 64-token KV
+        rt.policy.process(msg)
+        assert rt.activation_send_queue.empty()
+        assert rt.input_pool.pool.buffer_info[msg.pool_id].status.value == "free"
+        msg = token_message(rt, "y", [1, 2, 3])
+        msg.layer_id = 1                                         # layer 2 is not hosted here
+        rt.policy.process(msg)
+        assert rt.activation_send_queue.empty()
+        with pytest.raises(RuntimeError, match="not hosted"):
+            rt.model.apply_single_layer(3, torch.zeros(1, 1, cfgd["hidden_size"], dtype=torch.bfloat16, device="cuda"),
+                                        rt.get_or_make_kv("z").kv)
+        rt.model.unload_layers([0])
+        with pytest.raises(_cabi.DnError) as ei:
+            rt.model.apply_single_layer(0, torch.zeros(1, 1, cfgd["hidden_size"], dtype=torch.bfloat16, device="cuda"),
+                                        rt.get_or_make_kv("z").kv)
+        assert ei.value.code == _cabi.DN_ENOENT
+    finally:
+        rt.unload_model_core()
+
+
+def test_full_size_llama3_8b_dims_two_layers(cuda_lib):
+    """BASELINE config dims (H=4096, 32/8 heads, FFN 14336, V=128256) on a 2-layer slice:
+    oracle comparison + the split / graph properties at full width."""
+    from dnet_b200.shard.models import ShardLoadModelRequest
+    from dnet_b200.shard.runtime import ShardRuntime
+    from dnet_b200.utils.model import SyntheticSource, get_model_metadata
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+
+    cfgd = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=8, head_dim=128, intermediate_size=14336,
+                vocab_size=128256, num_hidden_layers=2, rms_norm_eps=1e-5, rope_theta=500000.0, model_type="llama",
+                tie_word_embeddings=False, torch_dtype="bfloat16")
+    src = SyntheticSource(cfgd, seed=0)
+
+    def load(layers, sid):
+        rt = ShardRuntime(shard_id=sid)
+        rt.kv_cache_config.max_tokens = 256
+        rt.load_model_core(ShardLoadModelRequest(model_path=src, total_layers=2, layers=layers, window_size=len(layers),
+                                                 residency_size=len(layers), kv_bits="fp16"))
+        return rt
+
+    one = load([0, 1], "one")
+    prompt = np.random.Generator(np.random.PCG64(1234)).integers(0, 128256, size=9).tolist()
+    try:
+        out = ring_generate([one], "n", prompt, 6)
+        f32, _ = one.model.head_logits(one._kv_by_nonce["n"].x1)
+        torch.cuda.synchronize()
+        # oracle on the same weights (device -> host copy of what the shard holds)
+        w = {}
+        for l in (0, 1):
+            for k, v in one.policy.weight_cache.cache[l][0].items():
+                if not k.startswith("_"):
+                    w["model." + k] = v.cpu()
+        for k, v in one._api_tensors.items():
+            w[("model." if not k.startswith("lm_head") else "") + k] = v.cpu()
+        oc = OracleConfig.from_dict(cfgd)
+        orc = LlamaOracle(oc, w)
+        kv = {0: OracleKV(), 1: OracleKV()}
+        ids = torch.tensor(prompt, dtype=torch.int32)
+        toks = []
+        for step in range(6):
+            x = orc.embed(ids)
+            for l in (0, 1):
+                x = orc.apply_single_layer(l, x, kv[l])
+            lf = orc.lm_project(orc.normalize(x[-1:]), return_fp32=True)[0]
+            top2 = torch.topk(lf, 2).values
+            toks.append((int(torch.argmax(lf.to(torch.bfloat16).float())), float(top2[0] - top2[1])))
+            ids = torch.tensor([out[step][0]], dtype=torch.int32)     # teacher-forced with the GPU ids
+        assert rel_inf(f32.cpu(), lf) <= LOGIT_TOL
+        for (tok, gap), (gt, _, _) in zip(toks, out):
+            if gap > 0.05:          # decided by more than bf16 rounding noise of a ~4.0 logit
+                assert tok == gt
+    finally:
+        one.unload_model_core()
+    a, b = load([0], "a"), load([1], "b")
+    try:
+        out2 = ring_generate([a, b], "n", prompt, 6)
+        assert [t for t, _, _ in out2] == [t for t, _, _ in out]       # split is bit-exact
+        assert [p for _, p, _ in out2] == [p for _, p, _ in out]
+    finally:
+        a.unload_model_core()
+        b.unload_model_core()
