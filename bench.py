@@ -239,6 +239,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                                              layers=list(range(L)), window_size=L, residency_size=L, kv_bits="fp16"))
     lib.dn_set_option(b"pdl", 1 if args.pdl else 0)
     lib.dn_set_option(b"l2_prefetch_kb", args.l2_prefetch_kb)
+    rt.use_megakernel = bool(args.megakernel)
     pol = rt.policy
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(0, cfg["vocab_size"], (PROMPT_LEN,), generator=g).tolist()
@@ -375,7 +376,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "config": {"workload": f"Llama-3-8B bf16 bs=1 decode, 1 shard x {L} layers (BASELINE configs[1] at 1 shard)",
                    "prompt_len": PROMPT_LEN, "kv": "fp16 paged (64-token pages)", "wire_dtype": "bf16",
                    "l2": "inputs larger than L2 (15.0 GB of weights per step vs 126 MB L2); no flush",
-                   "pdl": bool(args.pdl), "l2_prefetch_kb": args.l2_prefetch_kb, "cuda_graph": True,
+                   "pdl": bool(args.pdl), "l2_prefetch_kb": args.l2_prefetch_kb,
+                   "step_kernel": "k_shard_step (one persistent cooperative kernel per token)" if args.megakernel
+                   else "per-op kernels replayed as a CUDA graph",
+                   "step_error": int(lib.dn_step_error(rt.model._h, rt.compute_stream_ptr)),
                    "sequences_in_flight": 1},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
@@ -390,9 +394,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (invalid as a bench number)")
-    ap.add_argument("--pdl", type=int, default=int(os.environ.get("DNET_COMPUTE_PDL", "1")))
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("DNET_COMPUTE_PDL", "0")))
+    ap.add_argument("--megakernel", type=int, default=int(os.environ.get("DNET_COMPUTE_MEGAKERNEL", "1")))
     ap.add_argument("--l2-prefetch-kb", type=int, default=64)
     ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--in-flight", type=int, default=0, help="sequences in flight at N>1 (default N)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -86,6 +86,8 @@ _PROTOS = {
     "dn_embed": (_i, [_vp, _vp, _i, _vp, _vp]),
     "dn_layer_forward": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "dn_window_forward": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _i, _vp, _vp]),
+    "dn_shard_step": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "dn_step_error": (_i, [_vp, _vp]),
     "dn_layer_forward_timed": (_i, [_vp, _i, _vp, _i, _vp, _vp, C.POINTER(C.c_float)]),
     "dn_head_timed": (_i, [_vp, _vp, _i, _vp, C.POINTER(C.c_float)]),
     "dn_head_sample_greedy": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),

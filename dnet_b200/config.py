@@ -36,7 +36,8 @@ class ComputeSettings:  # reference config.py:80-105 (prefix DNET_COMPUTE_)
     input_pool_mb: int = field(default_factory=lambda: _env("DNET_COMPUTE_INPUT_POOL_MB", 512, int))
     output_pool_mb: int = field(default_factory=lambda: _env("DNET_COMPUTE_OUTPUT_POOL_MB", 512, int))
     cuda_graphs: bool = field(default_factory=lambda: _env("DNET_COMPUTE_CUDA_GRAPHS", True, bool))
-    pdl: bool = field(default_factory=lambda: _env("DNET_COMPUTE_PDL", True, bool))
+    pdl: bool = field(default_factory=lambda: _env("DNET_COMPUTE_PDL", False, bool))
+    megakernel: bool = field(default_factory=lambda: _env("DNET_COMPUTE_MEGAKERNEL", True, bool))
 
 
 @dataclass

@@ -175,6 +175,9 @@ class WeightCache:
             if layer_id in self.reference_counts:
                 self.reference_counts[layer_id] -= 1
             if release_event is not None:
+                old = self._release_events.get(layer_id)
+                if old is not None:
+                    self._destroy_event(old)
                 self._release_events[layer_id] = release_event
 
     def prefetch_to_ram(self, layer_id: int):

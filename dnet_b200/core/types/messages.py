@@ -37,6 +37,9 @@ class ActivationMessage:
     repetition_penalty: float = 1.0
     min_p: float = 0.0
     min_tokens_to_keep: int = 1
+    # dnet_b200 extension: torch.cuda.Event recorded after the kernels that produce ``tensor``
+    # were enqueued; a consumer on another stream orders itself after it (device hand-off)
+    ready_event: Optional[Any] = None
 
     @classmethod
     def from_proto(cls, proto_msg, pool_id: int = 0):

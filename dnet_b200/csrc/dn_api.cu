@@ -3,6 +3,7 @@
 // scratch buffers, launch geometry, CUDA graphs, the NVLink hop and the pinned->HBM
 // layer-swap copies.  All arithmetic is in dn_kernels.cuh.
 #include "dn_kernels.cuh"
+#include "dn_megakernel.cuh"
 #include "../../include/dnet_b200.h"
 
 #include <atomic>
@@ -95,6 +96,11 @@ struct dn_model {
   size_t page_elems = 0, layer_elems = 0;
   std::vector<int> free_pages;
   size_t max_smem = 0;
+  // megakernel state
+  std::vector<MkLayer> mk_host;
+  MkLayer* mk_dev = nullptr;
+  bf16 *xa = nullptr, *xb = nullptr;
+  unsigned int* mk_sync = nullptr;   // [0] barrier count, [1] generation, [2] error, [3] head ticket
 };
 
 struct dn_kv {
@@ -244,6 +250,15 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
     }
   }
   for (int p = cfg->kv_pool_pages - 1; p >= 0; --p) m->free_pages.push_back(p);
+  m->mk_host.resize(n_layers > 0 ? n_layers : 1);
+  memset(m->mk_host.data(), 0, m->mk_host.size() * sizeof(MkLayer));
+  for (int i = 0; i < n_layers; ++i) m->mk_host[i].kv_pool = m->kv_pool ? m->kv_pool + (size_t)i * m->layer_elems : nullptr;
+  CK(cudaMalloc(&m->mk_dev, m->mk_host.size() * sizeof(MkLayer)));
+  CK(cudaMemcpy(m->mk_dev, m->mk_host.data(), m->mk_host.size() * sizeof(MkLayer), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&m->xa, (size_t)H * 2));
+  CK(cudaMalloc(&m->xb, (size_t)H * 2));
+  CK(cudaMalloc(&m->mk_sync, 64));
+  CK(cudaMemset(m->mk_sync, 0, 64));
   *out = m;
   return DN_OK;
 }
@@ -252,6 +267,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   if (!m) return DN_OK;
   cudaFree(m->hbuf); cudaFree(m->qbuf); cudaFree(m->attn); cudaFree(m->act); cudaFree(m->logits_bf16);
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
+  cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
   delete m;
   return DN_OK;
 }
@@ -269,6 +285,9 @@ extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_
     if (((uintptr_t)L.w[i]) & 15) return fail(DN_EINVAL, "layer %d: tensor %d is not 16-byte aligned", abs_layer, i);
   }
   L.bound = true;
+  MkLayer& ML = m->mk_host[it->second];
+  for (int i = 0; i < DN_W_COUNT; ++i) ML.w[i] = L.w[i];
+  CK(cudaMemcpy(m->mk_dev + it->second, &ML, sizeof(MkLayer), cudaMemcpyHostToDevice));
   return DN_OK;
 }
 
@@ -277,6 +296,7 @@ extern "C" int dn_unbind_layer(dn_model* m, int abs_layer) {
   auto it = m->abs2local.find(abs_layer);
   if (it == m->abs2local.end()) return fail(DN_ENOENT, "layer %d not hosted on this model instance", abs_layer);
   m->layers[it->second].bound = false;
+  memset(m->mk_host[it->second].w, 0, sizeof(m->mk_host[it->second].w));
   memset(m->layers[it->second].w, 0, sizeof(m->layers[it->second].w));
   return DN_OK;
 }
@@ -520,6 +540,105 @@ extern "C" int dn_head_logits(dn_model* m, const void* x, int T, float* logits_f
 }
 
 // ---------------------------------------------------------------------------------
+// the single-token shard step as one persistent kernel (dn_megakernel.cuh)
+// ---------------------------------------------------------------------------------
+static int g_mk_smem_set = 0;
+template <int G>
+static cudaError_t launch_step(const MkParams& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  if (!(g_mk_smem_set & (1 << G))) {
+    e = cudaFuncSetAttribute(k_shard_step<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    g_mk_smem_set |= (1 << G);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(g_sms);
+  cfg.blockDim = dim3(MK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or the launch fails (never a deadlock)
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (g_capturing) g_capture_launches++;
+  else g_launches++;
+  return cudaLaunchKernelEx(&cfg, k_shard_step<G>, p);
+}
+
+extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                             int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
+                             float* logits_f32_out, int advance, dn_stream s) {
+  if (!m || !x_inout || !kv || n < 0 || (n > 0 && !abs_layers)) return fail(DN_EINVAL, "bad argument");
+  if (kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
+  if (n == 0 && !do_head) return fail(DN_EINVAL, "nothing to do");
+  if (!g_capturing && kv->host_pos + 1 > kv->max_tokens) return fail(DN_ENOSPC, "KV capacity exceeded");
+  int first_local = 0;
+  for (int i = 0; i < n; ++i) {
+    auto it = m->abs2local.find(abs_layers[i]);
+    if (it == m->abs2local.end()) return fail(DN_ENOENT, "Layer %d not hosted on this model instance", abs_layers[i]);
+    if (!m->layers[it->second].bound) return fail(DN_ENOENT, "layer %d has no weights bound", abs_layers[i]);
+    if (i == 0) first_local = it->second;
+    else if (it->second != first_local + i) return fail(DN_EINVAL, "dn_shard_step needs a contiguous run of local layers");
+  }
+  if (embed_from_token && !m->embed) return fail(DN_ENOENT, "embed_tokens not bound on this shard");
+  if (do_head && (!m->norm || !m->head)) return fail(DN_ENOENT, "final norm / lm_head not bound on this shard");
+  const dn_model_cfg& c = m->cfg;
+  MkParams p;
+  memset(&p, 0, sizeof(p));
+  p.layers = m->mk_dev + first_local;
+  p.n_layers = n;
+  p.H = c.hidden; p.FFN = c.ffn; p.n_heads = c.n_heads; p.n_kv = c.n_kv_heads; p.vocab = c.vocab; p.nsplit = m->nsplit;
+  p.eps = c.rms_eps;
+  p.x_in = (const bf16*)x_inout;
+  p.embed = embed_from_token ? m->embed : nullptr;
+  p.xa = m->xa; p.xb = m->xb; p.hbuf = m->hbuf; p.qbuf = m->qbuf; p.attn = m->attn; p.act = m->act;
+  p.x_out = (bf16*)x_inout;
+  p.block_table = kv->block_table; p.st = kv->st; p.inv_freq = m->inv_freq;
+  p.part = m->part; p.tickets = m->tickets;
+  p.norm_w = m->norm; p.head_w = m->head; p.logits_bf16 = m->logits_bf16; p.logits_f32 = logits_f32_out;
+  p.head_part = m->head_part; p.head_ticket = m->mk_sync + 3;
+  p.token_out = token_out; p.logprob_out = logprob_out; p.do_head = do_head ? 1 : 0; p.advance = advance ? 1 : 0;
+  p.bar_count = m->mk_sync; p.bar_gen = m->mk_sync + 1; p.err = m->mk_sync + 2;
+  const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
+  int scratch = kmax * 2;
+  const int attn_bytes = 2 * PAGE * HD * 2 + 8 * 32 * 4 + 64;
+  if (scratch < attn_bytes) scratch = attn_bytes;
+  scratch = (scratch + 1023) / 1024 * 1024;
+  const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4;
+  int stages = (227 * 1024 - 1024 - scratch - tail) / MK_STAGE_BYTES;
+  if (stages > MK_MAX_STAGES) stages = MK_MAX_STAGES;
+  if (stages < 2) return fail(DN_EINVAL, "model too wide for the megakernel's shared-memory ring");
+  p.n_stages = stages;
+  p.scratch_bytes = scratch;
+  const size_t smem = (size_t)stages * MK_STAGE_BYTES + scratch + tail;
+  if ((size_t)g_sms > (size_t)CTAS_PER_SM * g_sms) return fail(DN_EINVAL, "head partial buffer too small");
+  cudaError_t e;
+  switch (m->G) {
+    case 1: e = launch_step<1>(p, smem, (cudaStream_t)s); break;
+    case 2: e = launch_step<2>(p, smem, (cudaStream_t)s); break;
+    case 4: e = launch_step<4>(p, smem, (cudaStream_t)s); break;
+    case 5: e = launch_step<5>(p, smem, (cudaStream_t)s); break;
+    case 7: e = launch_step<7>(p, smem, (cudaStream_t)s); break;
+    case 8: e = launch_step<8>(p, smem, (cudaStream_t)s); break;
+    default: return fail(DN_EINVAL, "GQA group %d unsupported", m->G);
+  }
+  if (e != cudaSuccess) return fail(DN_ECUDA, "k_shard_step launch: %s", cudaGetErrorString(e));
+  if (advance && !g_capturing) kv->host_pos += 1;
+  return DN_OK;
+}
+
+// 0 = clean; 2/3 = a bounded spin inside k_shard_step timed out (results of that step are invalid)
+extern "C" int dn_step_error(dn_model* m, dn_stream s) {
+  if (!m) return fail(DN_EINVAL, "null model");
+  unsigned int v = 0;
+  CK(cudaMemcpyAsync(&v, m->mk_sync + 2, 4, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  CK(cudaStreamSynchronize((cudaStream_t)s));
+  return (int)v;
+}
+
+// ---------------------------------------------------------------------------------
 // graphs
 // ---------------------------------------------------------------------------------
 extern "C" int dn_graph_begin(dn_stream s) {
@@ -666,10 +785,10 @@ extern "C" int dn_event_elapsed_ms(dn_event a, dn_event b, float* ms) {
   return DN_OK;
 }
 extern "C" int dn_memcpy_h2d(void* dst, const void* src, size_t bytes, dn_stream s) {
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)s));
   return DN_OK;
 }
 extern "C" int dn_memcpy_d2h(void* dst, const void* src, size_t bytes, dn_stream s) {
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)s));   // dst may be pinned host or device
   return DN_OK;
 }

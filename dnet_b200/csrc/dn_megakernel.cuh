@@ -1,0 +1,628 @@
+// dn_megakernel.cuh -- the whole single-token shard step as ONE persistent kernel.
+//
+// Why: ncu on the per-op kernels (profiles/r01_*) shows every weight-streaming kernel moves
+// exactly its algorithmic bytes but is latency bound (59% long-scoreboard stalls, 16 warps/SM)
+// and pays ~10-14 us of launch + prologue + ramp + tail per launch, 160 launches per token.
+// This kernel removes both:
+//   * one CTA per SM (grid = #SMs), 9 warps: warp 8 is a PRODUCER that streams this CTA's
+//     share of every weight matrix of every layer through a shared-memory ring with TMA bulk
+//     copies (cp.async.bulk + mbarrier complete_tx): no registers are tied up by loads in
+//     flight, ~11 x 16 KB per SM are always outstanding, and because weights are immutable the
+//     producer never waits for a phase boundary -- HBM streams continuously across all the
+//     phases and layers of the step;
+//   * warps 0-7 are CONSUMERS: they wait on a stage's full-barrier, read the 32-row x 256-col
+//     bf16 tile from shared memory (each warp owns 4 rows of the tile, so there is no
+//     cross-warp reduction and no block barrier per row block), keep fp32 partial sums, and
+//     run the same fused epilogues as the per-op kernels (RoPE + paged-KV append, residual,
+//     SwiGLU, argmax/logsumexp);
+//   * phases that depend on activations produced by other CTAs are separated by a grid
+//     barrier among consumer warps only (sense-reversing, bounded spin so a bug can never
+//     hang the GPU); five per layer.
+// Rounding points and summation structure per output row are fixed -> deterministic.
+#pragma once
+#include "dn_kernels.cuh"
+
+namespace dn {
+
+constexpr int MK_CW = 8;                        // consumer warps
+constexpr int MK_CTHREADS = MK_CW * 32;         // 256
+constexpr int MK_THREADS = MK_CTHREADS + 32;    // + producer warp
+constexpr int MK_ROWS = 32;                     // rows per ring stage
+constexpr int MK_ROW_BYTES = 512;               // 256 bf16 columns per row per stage
+constexpr int MK_STAGE_BYTES = MK_ROWS * MK_ROW_BYTES;   // 16 KB
+constexpr int MK_MAX_STAGES = 12;
+constexpr unsigned long long MK_TIMEOUT_NS = 4000000000ull;  // bounded spins
+
+enum { MK_W_Q = 0, MK_W_K, MK_W_V, MK_W_O, MK_W_GATE, MK_W_UP, MK_W_DOWN, MK_W_LN1, MK_W_LN2, MK_W_QB, MK_W_KB, MK_W_VB, MK_W_N };
+
+struct MkLayer {
+  const bf16* w[MK_W_N];
+  bf16* kv_pool;          // this layer's pages
+};
+
+struct MkParams {
+  const MkLayer* layers;  // device array, execution order
+  int n_layers;
+  int H, FFN, n_heads, n_kv, vocab, nsplit;
+  float eps;
+  const bf16* x_in;       // [H]; ignored when embed != nullptr
+  const bf16* embed;      // first shard: x_in = embed[st->token]
+  bf16 *xa, *xb, *hbuf, *qbuf, *attn, *act;
+  bf16* x_out;            // [H] result of the last layer (may alias x_in)
+  const int32_t* block_table;
+  StepState* st;
+  const float* inv_freq;
+  float* part;
+  unsigned int* tickets;
+  const bf16 *norm_w, *head_w;
+  bf16* logits_bf16;
+  float* logits_f32;
+  HeadPartial* head_part;
+  unsigned int* head_ticket;
+  int32_t* token_out;
+  float* logprob_out;
+  int do_head, advance;
+  unsigned int *bar_count, *bar_gen, *err;
+  int n_stages;
+  int scratch_bytes;      // shared scratch (activation vector / attention tiles)
+};
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded wait: on timeout flag the error and fall through (garbage results, never a hang)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = gtimer();
+  unsigned it = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++it & 1023u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) {
+      atomicExch(err, 2u);
+      return;
+    }
+  }
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MK_CTHREADS) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// grid barrier among the consumer warps of all CTAs (all CTAs are co-resident: grid = #SMs,
+// one CTA per SM, launched cooperatively)
+__device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int& gen) {
+  cbar_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int arrived = atomicAdd(p.bar_count, 1u);
+    if (arrived == gridDim.x - 1) {
+      atomicExch(p.bar_count, 0u);
+      __threadfence();
+      atomicAdd(p.bar_gen, 1u);
+    } else {
+      const unsigned long long t0 = gtimer();
+      unsigned it = 0;
+      while (ld_acquire_gpu(p.bar_gen) == gen) {
+        if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) {
+          atomicExch(p.err, 3u);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  gen += 1;
+  cbar_sync();
+}
+
+// ---------------------------------------------------------------------------------
+// phase description shared by producer and consumers (identical traversal order)
+// ---------------------------------------------------------------------------------
+enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DOWN = 3, PH_HEAD = 4 };
+
+struct MkPhase {
+  int K, nrows, align;
+};
+__device__ __forceinline__ MkPhase mk_phase(const MkParams& p, int ph) {
+  MkPhase d;
+  switch (ph) {
+    case PH_QKV: d.K = p.H; d.nrows = (p.n_heads + 2 * p.n_kv) * HD; d.align = 2; break;
+    case PH_O: d.K = p.n_heads * HD; d.nrows = p.H; d.align = 1; break;
+    case PH_GU: d.K = p.H; d.nrows = 2 * p.FFN; d.align = 2; break;
+    case PH_DOWN: d.K = p.FFN; d.nrows = p.H; d.align = 1; break;
+    default: d.K = p.H; d.nrows = p.vocab; d.align = 1; break;
+  }
+  return d;
+}
+__device__ __forceinline__ const bf16* mk_row(const MkParams& p, const MkLayer& L, int ph, int vr, int K) {
+  switch (ph) {
+    case PH_QKV: {
+      const int task = vr >> 1, which = vr & 1;
+      const int slot = task >> 6, d = (task & 63) + (which << 6);
+      if (slot < p.n_heads) return L.w[MK_W_Q] + ((size_t)slot * HD + d) * K;
+      if (slot < p.n_heads + p.n_kv) return L.w[MK_W_K] + ((size_t)(slot - p.n_heads) * HD + d) * K;
+      return L.w[MK_W_V] + ((size_t)(slot - p.n_heads - p.n_kv) * HD + d) * K;
+    }
+    case PH_O: return L.w[MK_W_O] + (size_t)vr * K;
+    case PH_GU: return ((vr & 1) ? L.w[MK_W_UP] : L.w[MK_W_GATE]) + (size_t)(vr >> 1) * K;
+    case PH_DOWN: return L.w[MK_W_DOWN] + (size_t)vr * K;
+    default: return p.head_w + (size_t)vr * K;
+  }
+}
+__device__ __forceinline__ void mk_range(const MkPhase& d, int& r0, int& r1) {
+  const int units = d.nrows / d.align;
+  r0 = (int)(((long long)units * blockIdx.x) / gridDim.x) * d.align;
+  r1 = (int)(((long long)units * (blockIdx.x + 1)) / gridDim.x) * d.align;
+}
+
+struct MkRing {
+  unsigned char* data;   // n_stages * MK_STAGE_BYTES
+  uint64_t* full;        // [n_stages]
+  uint64_t* empty;       // [n_stages]
+  int n_stages;
+  int stage;
+  uint32_t phase;
+  __device__ __forceinline__ void advance() {
+    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// producer: stream one GEMV phase of this CTA through the ring
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mk_produce(const MkParams& p, const MkLayer& L, int ph, MkRing& ring, int lane) {
+  const MkPhase d = mk_phase(p, ph);
+  int r0, r1;
+  mk_range(d, r0, r1);
+  const int nchunks = d.K >> 8;
+  for (int rb = r0; rb < r1; rb += MK_ROWS) {
+    const int nv = min(MK_ROWS, r1 - rb);
+    const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
+      if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * MK_ROW_BYTES);
+      __syncwarp();
+      if (lane < nv)
+        tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + lane * MK_ROW_BYTES, src + (c << 8),
+                     MK_ROW_BYTES, &ring.full[ring.stage]);
+      ring.advance();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// consumer: one GEMV phase.  Epi is called by every lane with (vr, v, partner, valid); the
+// lanes with (lane & 7) == 0 are the row owners (4 rows per warp per block).
+// ---------------------------------------------------------------------------------
+template <class Epi>
+__device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ring, const bf16* xs, int cw, int lane,
+                                           Epi epi) {
+  const MkPhase d = mk_phase(p, ph);
+  int r0, r1;
+  mk_range(d, r0, r1);
+  const int nchunks = d.K >> 8;
+  for (int rb = r0; rb < r1; rb += MK_ROWS) {
+    const int nv = min(MK_ROWS, r1 - rb);
+    const int myrows = min(4, max(0, nv - 4 * cw));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&ring.full[ring.stage], ring.phase, p.err);
+      if (myrows > 0) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + (c << 8) + (lane << 3));
+        const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
+                             bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
+        const unsigned char* tile = ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (4 * cw) * MK_ROW_BYTES + lane * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < myrows) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(tile + j * MK_ROW_BYTES);
+            acc[j] = dot8(wv, xf, acc[j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
+      ring.advance();
+    }
+    // 4 values per lane -> lane group g = lane>>3 owns row 4*cw + (bit4*2 + bit3)
+    {
+      const bool up = (lane & 16) != 0;
+      const float k0 = up ? acc[2] : acc[0], k1 = up ? acc[3] : acc[1];
+      const float s0 = up ? acc[0] : acc[2], s1 = up ? acc[1] : acc[3];
+      acc[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+      acc[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    }
+    {
+      const bool up = (lane & 8) != 0;
+      const float k = up ? acc[1] : acc[0], s = up ? acc[0] : acc[1];
+      acc[0] = k + __shfl_xor_sync(0xffffffffu, s, 8);
+    }
+    float v = acc[0];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const int j = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    const int r_local = 4 * cw + j;
+    epi(rb + r_local, v, r_local < nv && (lane & 7) == 0);
+  }
+}
+
+// stage a bf16 vector [K] from global (produced by other CTAs: bypass L1) into shared memory
+__device__ __forceinline__ void mk_stage_copy(bf16* xs, const bf16* src, int K) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K / 8; i += MK_CTHREADS)
+    reinterpret_cast<uint4*>(xs)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
+  cbar_sync();
+}
+// RMSNorm staging (same arithmetic and summation structure as stage_rmsnorm<1>)
+__device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const bf16* src, const bf16* w, int K, float eps) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float ss = 0.f;
+  for (int i = tid * 8; i < K; i += MK_CTHREADS * 8) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
+    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  }
+  ss = warp_sum(ss);
+  cbar_sync();
+  if (lane == 0) scratch[warp] = ss;
+  cbar_sync();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MK_CW; ++i) tot += scratch[i];
+  const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+  for (int i = tid * 8; i < K; i += MK_CTHREADS * 8) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
+    const uint4 g = *reinterpret_cast<const uint4*>(w + i);
+    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+    const float gw[8] = {bf_lo(g.x), bf_hi(g.x), bf_lo(g.y), bf_hi(g.y), bf_lo(g.z), bf_hi(g.z), bf_lo(g.w), bf_hi(g.w)};
+    __align__(16) bf16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fmul_rn(bf16r(__fmul_rn(f[j], inv)), gw[j]));
+    *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(o);
+  }
+  cbar_sync();
+}
+
+// ---------------------------------------------------------------------------------
+// attention phase for one (kv head, split) task on the 256 consumer threads; warps < G compute
+// ---------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane) {
+  const int kv_len = p.st->pos + 1;
+  const int npages = (kv_len + PAGE - 1) / PAGE;
+  const int nact = min(p.nsplit, npages);            // active splits (short contexts use few)
+  const int task = blockIdx.x;
+  if (task >= p.n_kv * nact) return;                  // CTA-uniform
+  const int kvh = task / nact, sp = task % nact;
+  const int pps = (npages + nact - 1) / nact;
+  const int p0 = sp * pps, p1 = min(p0 + pps, npages);
+  bf16* Ks = reinterpret_cast<bf16*>(scratch);
+  bf16* Vs = Ks + PAGE * HD;
+  float* ps = reinterpret_cast<float*>(scratch + 2 * PAGE * HD * sizeof(bf16));   // [G][32]
+  int* s_last = reinterpret_cast<int*>(ps + G * 32);
+  const int head = kvh * G + cw;
+  const float scale = 0.08838834764831845f;
+  float qv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cw < G) {
+    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(p.qbuf + head * HD + lane * 4));
+    qv[0] = __fmul_rn(bf_lo(u.x), scale); qv[1] = __fmul_rn(bf_hi(u.x), scale);
+    qv[2] = __fmul_rn(bf_lo(u.y), scale); qv[3] = __fmul_rn(bf_hi(u.y), scale);
+  }
+  float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int pg = p0; pg < p1; ++pg) {
+    const int phys = p.block_table[pg];
+    const uint4* ksrc = reinterpret_cast<const uint4*>(L.kv_pool + (((size_t)phys * 2 + 0) * p.n_kv + kvh) * (PAGE * HD));
+    const uint4* vsrc = reinterpret_cast<const uint4*>(L.kv_pool + (((size_t)phys * 2 + 1) * p.n_kv + kvh) * (PAGE * HD));
+    const int ntok = min(PAGE, kv_len - pg * PAGE);
+    const int n16 = ntok * HD / 8;
+    for (int i = threadIdx.x; i < n16; i += MK_CTHREADS) {
+      reinterpret_cast<uint4*>(Ks)[i] = __ldcg(ksrc + i);
+      reinterpret_cast<uint4*>(Vs)[i] = __ldcg(vsrc + i);
+    }
+    cbar_sync();
+    if (cw < G) {
+#pragma unroll 1
+      for (int h0 = 0; h0 < ntok; h0 += 32) {
+        const int nt = min(32, ntok - h0);
+        float sc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sc[j] = 0.f;
+          if (j < nt) {
+            const uint2 u = *reinterpret_cast<const uint2*>(Ks + (h0 + j) * HD + lane * 4);
+            sc[j] = fmaf(qv[0], bf_lo(u.x), fmaf(qv[1], bf_hi(u.x), fmaf(qv[2], bf_lo(u.y), qv[3] * bf_hi(u.y))));
+          }
+        }
+        transpose_reduce32(sc, lane);
+        const bool valid = lane < nt;
+        const float s = valid ? sc[0] : -INFINITY;
+        const float m_new = fmaxf(m, warp_max(s));
+        const float pj = valid ? exp2f((s - m_new) * LOG2E) : 0.f;
+        const float corr = exp2f((m - m_new) * LOG2E);
+        l = l * corr + warp_sum(pj);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) o[dd] *= corr;
+        m = m_new;
+        ps[cw * 32 + lane] = pj;
+        __syncwarp();
+        for (int j = 0; j < nt; ++j) {
+          const float pw = ps[cw * 32 + j];
+          const uint2 u = *reinterpret_cast<const uint2*>(Vs + (h0 + j) * HD + lane * 4);
+          o[0] = fmaf(pw, bf_lo(u.x), o[0]); o[1] = fmaf(pw, bf_hi(u.x), o[1]);
+          o[2] = fmaf(pw, bf_lo(u.y), o[2]); o[3] = fmaf(pw, bf_hi(u.y), o[3]);
+        }
+        __syncwarp();
+      }
+    }
+    cbar_sync();
+  }
+  if (cw < G) {
+    float* pp = p.part + ((size_t)head * p.nsplit + sp) * PART_STRIDE;
+    *reinterpret_cast<float4*>(pp + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lane == 0) { pp[128] = m; pp[129] = l; }
+  }
+  __threadfence();
+  cbar_sync();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(&p.tickets[kvh], 1u);
+    *s_last = (old == (unsigned)nact - 1) ? 1 : 0;
+  }
+  cbar_sync();
+  if (!*s_last) return;
+  __threadfence();
+  if (cw < G) {
+    const float* hp = p.part + ((size_t)head * p.nsplit) * PART_STRIDE;
+    // lane s2 fetches split s2's (m, l) -> one round trip instead of nsplit dependent ones
+    const float ms = (lane < nact) ? __ldcg(hp + (size_t)lane * PART_STRIDE + 128) : -INFINITY;
+    const float ls = (lane < nact) ? __ldcg(hp + (size_t)lane * PART_STRIDE + 129) : 0.f;
+    const float M = warp_max(ms);
+    const float wgt = (ms == -INFINITY) ? 0.f : exp2f((ms - M) * LOG2E);
+    float Lsum = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s2 = 0; s2 < nact; ++s2) {               // fixed order -> deterministic
+      const float w2 = __shfl_sync(0xffffffffu, wgt, s2);
+      const float l2 = __shfl_sync(0xffffffffu, ls, s2);
+      if (w2 == 0.f) continue;
+      Lsum = fmaf(l2, w2, Lsum);
+      const float4 ov = __ldcg(reinterpret_cast<const float4*>(hp + (size_t)s2 * PART_STRIDE + lane * 4));
+      acc[0] = fmaf(ov.x, w2, acc[0]); acc[1] = fmaf(ov.y, w2, acc[1]);
+      acc[2] = fmaf(ov.z, w2, acc[2]); acc[3] = fmaf(ov.w, w2, acc[3]);
+    }
+    const float invL = 1.0f / Lsum;
+    __align__(8) bf16 ob[4];
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(acc[dd] * invL);
+    *reinterpret_cast<uint2*>(p.attn + head * HD + lane * 4) = *reinterpret_cast<const uint2*>(ob);
+  }
+  if (threadIdx.x == 0) p.tickets[kvh] = 0u;
+}
+
+// ---------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // layout: [ring n_stages*16K][scratch scratch_bytes][full[12]][empty[12]][red floats]
+  MkRing ring;
+  ring.data = smem;
+  ring.n_stages = p.n_stages;
+  unsigned char* scratch = smem + (size_t)p.n_stages * MK_STAGE_BYTES;
+  ring.full = reinterpret_cast<uint64_t*>(scratch + p.scratch_bytes);
+  ring.empty = ring.full + MK_MAX_STAGES;
+  float* red = reinterpret_cast<float*>(ring.empty + MK_MAX_STAGES);   // [64] misc scratch
+  ring.stage = 0;
+  ring.phase = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&ring.full[i], 1);
+      mbar_init(&ring.empty[i], MK_CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == MK_CW) {
+    // ===== PRODUCER: never waits for activations; runs ahead across phases and layers =====
+    for (int li = 0; li < p.n_layers; ++li) {
+      const MkLayer L = p.layers[li];
+      mk_produce(p, L, PH_QKV, ring, lane);
+      mk_produce(p, L, PH_O, ring, lane);
+      mk_produce(p, L, PH_GU, ring, lane);
+      mk_produce(p, L, PH_DOWN, ring, lane);
+    }
+    if (p.do_head) {
+      MkLayer dummy = p.layers[0];
+      mk_produce(p, dummy, PH_HEAD, ring, lane);
+    }
+    return;
+  }
+
+  // ===== CONSUMERS =====
+  const int cw = warp;
+  bf16* xs = reinterpret_cast<bf16*>(scratch);
+  unsigned int gen = 0;
+  if (threadIdx.x == 0) gen = ld_acquire_gpu(p.bar_gen);
+  const int pos = p.st->pos;
+  const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(p.st->token, 0), p.vocab - 1) * p.H : p.x_in;
+
+  for (int li = 0; li < p.n_layers; ++li) {
+    const MkLayer L = p.layers[li];
+    bf16* nxt = (li == p.n_layers - 1) ? p.x_out : ((li & 1) ? p.xb : p.xa);
+
+    // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
+    mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
+    mk_consume(p, PH_QKV, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+      const int task = vr >> 1, which = vr & 1;
+      const int slot = task >> 6, d = task & 63;
+      int kind = 0, hrow = slot;
+      if (slot >= p.n_heads + p.n_kv) { kind = 2; hrow = slot - p.n_heads - p.n_kv; }
+      else if (slot >= p.n_heads) { kind = 1; hrow = slot - p.n_heads; }
+      const int dim = d + (which << 6);
+      const bf16* bias = L.w[kind == 0 ? MK_W_QB : (kind == 1 ? MK_W_KB : MK_W_VB)];
+      if (owner && bias != nullptr) v += __bfloat162float(bias[hrow * HD + dim]);
+      const float y = bf16r(v);
+      const float yp = __shfl_xor_sync(0xffffffffu, y, 8);
+      if (!owner) return;
+      float o = y;
+      if (kind != 2) {
+        const float theta = __fmul_rn((float)pos, p.inv_freq[d]);
+        float sn, cs;
+        sincosf(theta, &sn, &cs);
+        o = which == 0 ? __fsub_rn(__fmul_rn(y, cs), __fmul_rn(yp, sn)) : __fadd_rn(__fmul_rn(yp, sn), __fmul_rn(y, cs));
+        o = bf16r(o);
+      }
+      if (kind == 0) {
+        p.qbuf[hrow * HD + dim] = __float2bfloat16_rn(o);
+      } else {
+        const int page = p.block_table[pos / PAGE];
+        const size_t off = (((size_t)page * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
+        L.kv_pool[off] = __float2bfloat16_rn(o);
+      }
+    });
+    mk_grid_barrier(p, gen);
+
+    // ---- P2: paged-KV attention (split over pages, last-CTA merge)
+    mk_attention<G>(p, L, scratch, cw, lane);
+    mk_grid_barrier(p, gen);
+
+    // ---- P3: o_proj + residual
+    mk_stage_copy(xs, p.attn, p.n_heads * HD);
+    mk_consume(p, PH_O, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+      if (!owner) return;
+      const float o = bf16r(v);
+      const unsigned short xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
+      p.hbuf[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(xb_)), o));
+    });
+    mk_grid_barrier(p, gen);
+
+    // ---- P4: RMSNorm -> gate/up -> SwiGLU
+    mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
+    mk_consume(p, PH_GU, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+      const float y = bf16r(v);
+      const float u = __shfl_xor_sync(0xffffffffu, y, 8);
+      if (!owner || (vr & 1)) return;
+      const float s = bf16r(1.0f / (1.0f + expf(-y)));
+      const float a = bf16r(__fmul_rn(y, s));
+      p.act[vr >> 1] = __float2bfloat16_rn(__fmul_rn(a, u));
+    });
+    mk_grid_barrier(p, gen);
+
+    // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
+    mk_stage_copy(xs, p.act, p.FFN);
+    mk_consume(p, PH_DOWN, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+      if (!owner) return;
+      const float o = bf16r(v);
+      const unsigned short hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
+      nxt[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(hb)), o));
+    });
+    mk_grid_barrier(p, gen);
+    cur = nxt;
+  }
+
+  if (p.do_head) {
+    // ---- final RMSNorm -> lm_head -> bf16 logits -> greedy sample
+    mk_stage_rmsnorm(xs, red, cur, p.norm_w, p.H, p.eps);
+    float hm = -INFINITY, hl = 0.f;
+    int hi = 0x7fffffff;
+    mk_consume(p, PH_HEAD, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+      if (!owner) return;
+      const float lg = bf16r(v);
+      p.logits_bf16[vr] = __float2bfloat16_rn(v);
+      if (p.logits_f32 != nullptr) p.logits_f32[vr] = v;
+      if (lg > hm) { hl = hl * exp2f((hm - lg) * LOG2E) + 1.0f; hm = lg; hi = vr; }
+      else hl += exp2f((lg - hm) * LOG2E);
+    });
+    // merge (m, l, idx) over the warp, then over the 8 consumer warps, then over CTAs
+    auto merge = [](float& m, float& l, int& idx, float om, float ol, int oi) {
+      const float nm = fmaxf(m, om);
+      const float a = (m == -INFINITY) ? 0.f : l * exp2f((m - nm) * LOG2E);
+      const float b = (om == -INFINITY) ? 0.f : ol * exp2f((om - nm) * LOG2E);
+      l = a + b;
+      if (om > m || (om == m && oi < idx)) idx = oi;
+      m = nm;
+    };
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, hm, s);
+      const float ol = __shfl_xor_sync(0xffffffffu, hl, s);
+      const int oi = __shfl_xor_sync(0xffffffffu, hi, s);
+      merge(hm, hl, hi, om, ol, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red);
+    if (lane == 0) { red[cw] = hm; red[8 + cw] = hl; redi[16 + cw] = hi; }
+    cbar_sync();
+    if (threadIdx.x == 0) {
+      float m = red[0], l = red[8]; int idx = redi[16];
+      for (int w = 1; w < MK_CW; ++w) merge(m, l, idx, red[w], red[8 + w], redi[16 + w]);
+      HeadPartial hp; hp.m = m; hp.l = l; hp.idx = idx; hp.pad = 0;
+      p.head_part[blockIdx.x] = hp;
+      __threadfence();
+      const unsigned int old = atomicAdd(p.head_ticket, 1u);
+      redi[32] = (old == gridDim.x - 1) ? 1 : 0;
+    }
+    cbar_sync();
+    if (redi[32] && warp == 0) {
+      __threadfence();
+      float m = -INFINITY, l = 0.f; int idx = 0x7fffffff;
+      for (int i = lane; i < (int)gridDim.x; i += 32)
+        merge(m, l, idx, __ldcg(&p.head_part[i].m), __ldcg(&p.head_part[i].l), __ldcg(&p.head_part[i].idx));
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, s);
+        const float ol = __shfl_xor_sync(0xffffffffu, l, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, s);
+        merge(m, l, idx, om, ol, oi);
+      }
+      if (lane == 0) {
+        const float lse = bf16r(m + logf(l));
+        const float lp = bf16r(__fsub_rn(m, lse));
+        if (p.token_out != nullptr) *p.token_out = idx;
+        if (p.logprob_out != nullptr) *p.logprob_out = lp;
+        p.st->token = idx;
+        *p.head_ticket = 0u;
+        __threadfence_system();
+      }
+    }
+  }
+  if (p.advance && blockIdx.x == 0 && threadIdx.x == 0) p.st->pos = pos + 1;
+}
+
+}  // namespace dn

@@ -75,8 +75,11 @@ class ActivationCodec:
             shaped = output_buffer[:data_size].reshape(msg.shape)
         if shaped.dtype != self.runtime._wire_mx_dtype:
             shaped = shaped.to(self.runtime._wire_mx_dtype)
-        if shaped.is_cuda and getattr(self.runtime, "compute_stream", None) is not None:
-            self.runtime.compute_stream.synchronize()
+        if shaped.is_cuda:
+            if getattr(msg, "ready_event", None) is not None:
+                msg.ready_event.synchronize()
+            elif getattr(self.runtime, "compute_stream", None) is not None:
+                self.runtime.compute_stream.synchronize()
         data = tensor_to_bytes(shaped)
         msg.tensor = None
         return data

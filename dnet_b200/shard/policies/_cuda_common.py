@@ -53,6 +53,10 @@ def stage_input(rt, msg: ActivationMessage, ns) -> Optional[Tuple[torch.Tensor, 
     if msg.tensor is not None and msg.dtype != "tokens":
         src = msg.tensor.reshape(-1, H)
         T = src.shape[0]
+        if msg.ready_event is not None:
+            rt.compute_stream.wait_event(msg.ready_event)
+        else:   # unknown producer stream: order after everything enqueued on the current stream
+            rt.compute_stream.wait_stream(torch.cuda.current_stream())
         x = ns.x_view(T)
         if src.data_ptr() != x.data_ptr():
             if src.dtype != torch.bfloat16:
@@ -120,7 +124,9 @@ def build_output(rt, msg: ActivationMessage, x: torch.Tensor, last_layer: int, f
     if final is not None:
         return ActivationMessage(**common, is_final=True, token_id=final.token_id, logprob=final.logprob,
                                  top_logprobs=final.top_logprobs)
-    return ActivationMessage(**common, tensor=x.view(shape), req_logprobs=msg.req_logprobs,
+    ev = torch.cuda.Event()
+    ev.record(rt.compute_stream)
+    return ActivationMessage(**common, tensor=x.view(shape), ready_event=ev, req_logprobs=msg.req_logprobs,
                              req_top_logprobs=msg.req_top_logprobs, temperature=msg.temperature, top_p=msg.top_p,
                              top_k=msg.top_k, repetition_penalty=msg.repetition_penalty, min_p=msg.min_p,
                              min_tokens_to_keep=msg.min_tokens_to_keep)

@@ -48,6 +48,13 @@ class FitInMemoryPolicy(ComputePolicy):
         rt = self.runtime
         lib = _cabi.load()
         s = rt.compute_stream_ptr
+        if rt.use_megakernel:
+            # one persistent cooperative kernel for the whole step (dn_megakernel.cuh)
+            arr = (C.c_int32 * len(run))(*run)
+            _cabi.check(lib.dn_shard_step(rt.model._h, arr, len(run), x.data_ptr(), ns.kv._h, int(is_tokens),
+                                          int(fused_head), ns.result_token_ptr if fused_head else None,
+                                          ns.result_logprob_ptr if fused_head else None, None, 1, s))
+            return
         key = (run[0], is_tokens, fused_head)
         g = ns.graphs.get(key)
         if g is None:
@@ -109,7 +116,7 @@ class FitInMemoryPolicy(ComputePolicy):
 
                 # 3) stage x, 4) compute the run
                 final = None
-                use_graph = rt.use_cuda_graphs and T == 1 and self.window_size >= len(run)
+                use_graph = (rt.use_cuda_graphs or rt.use_megakernel) and T == 1 and self.window_size >= len(run)
                 if use_graph:
                     is_tokens = msg.dtype == "tokens"
                     if is_tokens:

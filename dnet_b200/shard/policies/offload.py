@@ -155,9 +155,8 @@ class OffloadPolicy(ComputePolicy):
 
                     rt.model.window_forward(window_layers, x, ns.kv, rt.compute_stream_ptr)
                     last_layer = window_layers[-1]
-                    ev = cc.release_event(rt)
                     for lid in window_layers:
-                        self.weight_cache.decrease_reference(lid, release_event=ev)
+                        self.weight_cache.decrease_reference(lid, release_event=cc.release_event(rt))
 
                     # eviction (reference offload.py:253-312)
                     try:

@@ -1,0 +1,131 @@
+"""Ring hop data plane over NVLink 5 / NVSwitch (replaces the tensor bytes of
+RingAdapter._send_activation + DnetRingService.StreamActivations, reference
+src/dnet/shard/adapters/ring.py:265-299, shard/grpc_servicer/servicer.py:129-161).
+
+One process per GPU, like dnet-shard.  The RECEIVING shard owns, per in-flight nonce slot,
+an HBM activation slot and a 32-bit sequence flag; both are exported with CUDA IPC once at
+``configure_topology`` time.  A hop is ``dn_hop_send``: one peer ``cudaMemcpyAsync`` into the
+next shard's slot on the sender's stream followed by a system-scope release store of the
+sequence number; the receiver's compute stream runs ``dn_hop_wait`` (a one-thread acquire
+spin, bounded by a timeout so a dead peer can never hang the GPU) and then computes straight
+out of the slot.  No host thread, protobuf, HTTP/2 or TCP on the tensor path; the gRPC
+frame of the reference still carries nonce / decoding parameters / ACKs (control plane).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+from dnet_b200 import _cabi
+
+
+class _CudaView:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_view(ptr: int, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+    """A torch tensor aliasing ``ptr`` (no ownership)."""
+    if dtype == torch.bfloat16:
+        n = 1
+        for s in shape:
+            n *= s
+        raw = torch.as_tensor(_CudaView(ptr, (n,), "<i2"), device="cuda")
+        return raw.view(torch.bfloat16).view(shape)
+    typestr = {torch.int32: "<i4", torch.uint8: "|u1", torch.float32: "<f4", torch.int16: "<i2"}[dtype]
+    return torch.as_tensor(_CudaView(ptr, shape, typestr), device="cuda")
+
+
+@dataclass
+class HopEndpoint:
+    """What a shard publishes to its ring predecessor (picklable: two 64-byte IPC handles)."""
+    data_handle: bytes
+    flag_handle: bytes
+    n_slots: int
+    slot_bytes: int
+
+
+class HopReceiver:
+    """Receiver-owned slots: ``n_slots`` x ``slot_bytes`` of HBM + one uint32 flag each (+1 error flag)."""
+
+    def __init__(self, n_slots: int, slot_bytes: int):
+        self.lib = _cabi.load()
+        self.n_slots, self.slot_bytes = n_slots, slot_bytes
+        d, f = C.c_void_p(), C.c_void_p()
+        _cabi.check(self.lib.dn_hop_alloc(n_slots * slot_bytes, C.byref(d)))
+        _cabi.check(self.lib.dn_hop_alloc((n_slots + 1) * 64, C.byref(f)))   # one 64-byte line per flag
+        self.data_ptr, self.flag_ptr = d.value, f.value
+
+    def slot(self, i: int) -> int:
+        return self.data_ptr + i * self.slot_bytes
+
+    def flag(self, i: int) -> int:
+        return self.flag_ptr + i * 64
+
+    @property
+    def err_flag(self) -> int:
+        return self.flag_ptr + self.n_slots * 64
+
+    def endpoint(self) -> HopEndpoint:
+        hd, hf = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+        _cabi.check(self.lib.dn_hop_export(self.data_ptr, hd))
+        _cabi.check(self.lib.dn_hop_export(self.flag_ptr, hf))
+        return HopEndpoint(bytes(hd), bytes(hf), self.n_slots, self.slot_bytes)
+
+    def wait(self, i: int, seq: int, stream: int, timeout_ms: int = 20000) -> None:
+        _cabi.check(self.lib.dn_hop_wait(self.flag(i), seq, timeout_ms, self.err_flag, stream))
+
+    def set_local(self, i: int, seq: int, stream: int) -> None:
+        """publish a sequence number on one of OUR OWN flags (e.g. prefilled inputs)."""
+        _cabi.check(self.lib.dn_hop_send(self.slot(i), self.slot(i), 0, self.flag(i), seq, stream))
+
+    def timed_out(self) -> bool:
+        return bool(int(device_view(self.err_flag, (1,), torch.int32).item()))
+
+    def free(self) -> None:
+        self.lib.dn_hop_free(self.data_ptr)
+        self.lib.dn_hop_free(self.flag_ptr)
+
+
+class HopSender:
+    """The sending side of one ring link: the peer's slots mapped into this process."""
+
+    def __init__(self, ep: HopEndpoint, same_process_ptrs: Optional[Tuple[int, int]] = None):
+        self.lib = _cabi.load()
+        self.ep = ep
+        self._imported = same_process_ptrs is None
+        if same_process_ptrs is not None:          # self-loop / single process: no IPC needed
+            self.data_ptr, self.flag_ptr = same_process_ptrs
+        else:
+            d, f = C.c_void_p(), C.c_void_p()
+            hd = (C.c_uint8 * 64).from_buffer_copy(ep.data_handle)
+            hf = (C.c_uint8 * 64).from_buffer_copy(ep.flag_handle)
+            _cabi.check(self.lib.dn_hop_import(hd, C.byref(d)))
+            _cabi.check(self.lib.dn_hop_import(hf, C.byref(f)))
+            self.data_ptr, self.flag_ptr = d.value, f.value
+
+    def send(self, i: int, src_ptr: int, nbytes: int, seq: int, stream: int) -> None:
+        _cabi.check(self.lib.dn_hop_send(self.data_ptr + i * self.ep.slot_bytes, src_ptr, nbytes,
+                                         self.flag_ptr + i * 64, seq, stream))
+
+    def close(self) -> None:
+        if self._imported:
+            self.lib.dn_hop_close(self.data_ptr)
+            self.lib.dn_hop_close(self.flag_ptr)
+
+
+def even_split(num_layers: int, world: int) -> List[List[int]]:
+    """contiguous equal splits, k=1 (the manual topology the benchmarks use; HALDA does not
+    balance identical devices)."""
+    base, rem = divmod(num_layers, world)
+    out, s = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append(list(range(s, s + n)))
+        s += n
+    return out

@@ -62,7 +62,8 @@ class NonceState:
         self.result_f32 = res.view(torch.float32)
         self.result_token_ptr = res.data_ptr()
         self.result_logprob_ptr = res.data_ptr() + 4
-        self.x1 = torch.zeros(1, model.hidden_size, dtype=torch.bfloat16, device="cuda")  # stable graph address
+        self.x1 = torch.empty(1, model.hidden_size, dtype=torch.bfloat16, device="cuda")  # stable graph address
+        # (torch.empty: no fill kernel on the default stream racing the compute stream)
 
     def x_view(self, T: int) -> torch.Tensor:
         if T == 1:
@@ -130,6 +131,7 @@ class ShardRuntime:
         self.compute_stream: Optional[torch.cuda.Stream] = None
         self.compute_stream_ptr: int = 0
         self.use_cuda_graphs: bool = bool(self._compute_settings.cuda_graphs)
+        self.use_megakernel: bool = bool(self._compute_settings.megakernel)
         self.stage_host: bool = True
         self._api_tensors: Dict[str, torch.Tensor] = {}
 
@@ -235,6 +237,7 @@ class ShardRuntime:
         self._api_tensors = api
         if api:
             self.model.load_weights(list(api.items()), strict=False)
+        torch.cuda.synchronize()   # loads ran on torch's current stream; compute runs on compute_stream
 
     def unload_model_core(self) -> ShardUnloadModelResponse:
         try:

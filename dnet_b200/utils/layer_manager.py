@@ -161,6 +161,7 @@ class LayerManager:
                 self.source.fill_device(self.weight_info[layer_idx][e.suffix], data[f"layers.{layer_idx}.{e.suffix}"])
             data["_slot"] = slot
             data["_ready_event"] = None
+            torch.cuda.current_stream().synchronize()   # generated on torch's stream, consumed on compute_stream
             return data
         rec = self._host_record(layer_idx)
         if stream is None:

@@ -117,6 +117,16 @@ int dn_layer_forward(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv
 /* the window loop of FitInMemoryPolicy.process (fit_in_memory.py:78-124) in one call */
 int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, int T,
                       dn_kv* kv, dn_stream s);
+/* The whole single-token step of this shard -- [embed] + a contiguous run of local layers +
+ * [final norm + lm_head + greedy sample] + [offset += 1] -- as ONE persistent cooperative
+ * kernel (TMA-fed weight ring, grid barriers between phases; dn_megakernel.cuh).  Same
+ * semantics as dn_embed + dn_window_forward + dn_head_sample_greedy + dn_kv_advance with T=1
+ * (FitInMemoryPolicy.process for a decode message, fit_in_memory.py:34-209).  With
+ * embed_from_token the input is embed_tokens[step-state token] and x_inout is output only. */
+int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                  int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
+                  float* logits_f32_out, int advance, dn_stream s);
+int dn_step_error(dn_model* m, dn_stream s);      /* 0, or the code of a timed-out in-kernel wait */
 /* measurement hooks for bench.py: per-kernel device times (CUDA events on stream s between
  * the five launches of one layer: qkv+rope+append, attention, o_proj, gate/up, down) */
 int dn_layer_forward_timed(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s,

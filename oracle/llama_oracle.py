@@ -136,12 +136,18 @@ class LlamaOracle:
     HF structural cross-check)."""
 
     def __init__(self, cfg: OracleConfig, weights: Dict[str, torch.Tensor], dtype=torch.bfloat16,
-                 exact_linear: bool = False):
+                 exact_linear: bool = False, f64_linear: bool = False):
         self.cfg = cfg
         self.dtype = dtype
         self.w = weights  # HF-style names, storage dtype
         self.inv_freq = rope_inv_freq(cfg)
         self.exact_linear = exact_linear
+        # f64_linear: accumulate the dot products in float64 (a second, equally valid summation
+        # order).  Used only to measure the oracle's own order-sensitivity ("noise floor"):
+        # every bf16 rounding point can flip by one ulp when the accumulation order changes,
+        # and downstream layers amplify a flip, so two correct implementations of this bf16
+        # pipeline do not agree to 1e-3 end to end (DESIGN.md section "parity").
+        self.f64_linear = f64_linear
 
     # -- primitives ---------------------------------------------------------
     def T(self, x: torch.Tensor) -> torch.Tensor:
@@ -149,6 +155,11 @@ class LlamaOracle:
 
     def linear(self, x: torch.Tensor, name: str, bias: Optional[str] = None) -> torch.Tensor:
         W = self.w[name]
+        if self.f64_linear:
+            y = (x.to(torch.float64) @ W.to(torch.float64).T)
+            if bias is not None and bias in self.w:
+                y = y + self.w[bias].to(torch.float64)
+            return self.T(y.to(torch.float32) if self.dtype == torch.float32 else y)
         if self.exact_linear or self.dtype == torch.float32:
             y = x.to(torch.float32) @ W.to(torch.float32).T
         else:

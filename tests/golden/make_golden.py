@@ -40,22 +40,25 @@ def bf16_ulp(x: float) -> float:
     return 2.0 ** (math.floor(math.log2(abs(x))) - 7) if x != 0 else 0.0
 
 
-def run(cfgd: dict, wseed: int, pseed: int, prompt_len: int, steps: int):
+def run(cfgd: dict, wseed: int, pseed: int, prompt_len: int, steps: int, f64: bool = False, force=None):
     cfg = OracleConfig.from_dict(cfgd)
     w = make_weights(cfg, wseed)
-    m = LlamaOracle(cfg, w, torch.bfloat16, exact_linear=True)
+    m = LlamaOracle(cfg, w, torch.bfloat16, exact_linear=True, f64_linear=f64)
     g = np.random.Generator(np.random.PCG64([pseed, 77]))
     prompt = g.integers(0, cfg.vocab_size, size=prompt_len).astype(np.int32)
     kv = {l: OracleKV() for l in range(cfg.num_hidden_layers)}
     ids = torch.from_numpy(prompt)
-    hidden_prefill = []
+    hidden_prefill, hidden_all = [], []
     toks, lps, gaps, logits_f32, logits_bf16 = [], [], [], [], []
     for step in range(steps):
         x = m.embed(ids)
+        if step == 0:
+            hidden_all.append(x.view(torch.int16).numpy().copy())
         for l in range(cfg.num_hidden_layers):
             x = m.apply_single_layer(l, x, kv[l])
             if step == 0:
                 hidden_prefill.append(x[-1].view(torch.int16).numpy().copy())
+                hidden_all.append(x.view(torch.int16).numpy().copy())
         y = m.normalize(x[-1:])
         lf = m.lm_project(y, return_fp32=True)[0]
         lb = lf.to(torch.bfloat16)
@@ -67,8 +70,8 @@ def run(cfgd: dict, wseed: int, pseed: int, prompt_len: int, steps: int):
         lps.append(r.logprob)
         logits_f32.append(lf.numpy().copy())
         logits_bf16.append(lb.view(torch.int16).numpy().copy())
-        ids = torch.tensor([r.token_id], dtype=torch.int32)
-    return dict(prompt=prompt, tokens=np.array(toks, np.int32), logprobs=np.array(lps, np.float32),
+        ids = torch.tensor([r.token_id if force is None else int(force[step])], dtype=torch.int32)
+    return dict(hidden_all=np.stack(hidden_all), prompt=prompt, tokens=np.array(toks, np.int32), logprobs=np.array(lps, np.float32),
                 gap_ulps=np.array(gaps, np.float32), logits_f32=np.stack(logits_f32),
                 logits_bf16=np.stack(logits_bf16), hidden_prefill=np.stack(hidden_prefill))
 
@@ -78,9 +81,14 @@ def search(name: str, cfgd: dict, wseed: int, prompt_len: int, steps: int, max_t
         out = run(cfgd, wseed, pseed, prompt_len, steps)
         if float(out["gap_ulps"].min()) >= MARGIN_ULPS:
             import json
+            # the oracle's own summation-order sensitivity, teacher-forced on the same tokens
+            alt = run(cfgd, wseed, pseed, prompt_len, steps, f64=True, force=out["tokens"])
+            a, b = torch.from_numpy(alt["logits_f32"]).double(), torch.from_numpy(out["logits_f32"]).double()
+            out["noise_floor"] = ((a - b).abs().amax(dim=1) / b.abs().amax(dim=1)).float().numpy()
             np.savez_compressed(Path(__file__).parent / f"{name}.npz", config=json.dumps(cfgd), wseed=wseed,
                                 pseed=pseed, steps=steps, **out)
-            print(name, "pseed", pseed, "min gap (bf16 ulps)", float(out["gap_ulps"].min()), "tokens", out["tokens"][:8])
+            print(name, "pseed", pseed, "min gap (bf16 ulps)", float(out["gap_ulps"].min()), "tokens", out["tokens"][:8],
+                  "noise floor max", float(out["noise_floor"].max()))
             return
     raise SystemExit(f"no margin-safe prompt found for {name}")
 

@@ -28,7 +28,7 @@ def oracle_weights(cfgd: dict, wseed: int, layers=None):
 
 def make_runtime(cfgd: dict, weights: Dict[str, torch.Tensor], layers: Sequence[int], *, shard_id="s0",
                  window_size: Optional[int] = None, residency_size: Optional[int] = None, cuda_graphs: bool = True,
-                 max_tokens: int = 512):
+                 max_tokens: int = 512, megakernel: bool = True):
     """A ShardRuntime loaded through the reference-facing path (load_model_core)."""
     from dnet_b200.shard.models import ShardLoadModelRequest
     from dnet_b200.shard.runtime import ShardRuntime
@@ -37,6 +37,7 @@ def make_runtime(cfgd: dict, weights: Dict[str, torch.Tensor], layers: Sequence[
     rt = ShardRuntime(shard_id=shard_id, queue_size=64)
     rt.kv_cache_config.max_tokens = max_tokens
     rt.use_cuda_graphs = cuda_graphs
+    rt.use_megakernel = megakernel
     n = len(layers)
     req = ShardLoadModelRequest(model_path=HostDictSource(weights, cfgd), total_layers=cfgd["num_hidden_layers"],
                                 layers=list(layers), window_size=window_size or n,
@@ -69,6 +70,8 @@ def forward_message(msg, use_bytes_rt=None):
     from dnet_b200.utils.serialization import tensor_to_bytes
 
     rt = use_bytes_rt
+    if msg.ready_event is not None:
+        msg.ready_event.synchronize()
     data = tensor_to_bytes(msg.tensor)
     shape = tuple(msg.shape)
     n = int(np.prod(shape))

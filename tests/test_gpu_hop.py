@@ -18,6 +18,7 @@ def test_hop_send_wait_and_bounded_timeout(cuda_lib):
     src = torch.arange(4096, dtype=torch.int16, device="cuda")
     dst_view = torch.empty(4096, dtype=torch.int16).pin_memory()
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()          # tensors above were made on torch's stream
     # receiver first: waits on seq 1, then copies the slot out
     _cabi.check(lib.dn_hop_wait(flags.value, 1, 2000, err.data_ptr(), s_rx.cuda_stream))
     _cabi.check(lib.dn_memcpy_d2h(dst_view.data_ptr(), slot.value, 8192, s_rx.cuda_stream))

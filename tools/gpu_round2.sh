@@ -1,0 +1,12 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -rf --tb=short > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -60 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 128 --warmup 8 --megakernel 1 > gpurun_out/bench_mk1.json 2> gpurun_out/bench_mk1.err; echo "bench exit $?"; tail -8 gpurun_out/bench_mk1.err; cat gpurun_out/bench_mk1.json
+timeout 400 python bench.py --steps 128 --warmup 8 --megakernel 0 --no-cpu > gpurun_out/bench_mk0.json 2> gpurun_out/bench_mk0.err; tail -4 gpurun_out/bench_mk0.err
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_shard_step' -s 6 -c 1 -o gpurun_out/prof_step python bench.py --steps 2 --warmup 3 --prompt-len 4 --no-e2e --no-cpu --megakernel 1 > gpurun_out/ncu_step.log 2>&1
+tail -3 gpurun_out/ncu_step.log
+ls -la gpurun_out
