@@ -177,7 +177,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                 run_step(n)
                 if use_ipc:
                     if last:
-                        tx.send(n, tok_local.data_ptr() + n * 64, 4, st + 2, s)      # token for the NEXT step
+                        tx.send(n, tok_local.data_ptr() + n * 64, 16, st + 2, s)     # token (16-byte line) for the NEXT step
                     else:
                         tx.send(n, graphs[n][1], slot_bytes, st + 1, s)
                 else:

@@ -607,7 +607,7 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   if (scratch < attn_bytes) scratch = attn_bytes;
   scratch = (scratch + 1023) / 1024 * 1024;
   const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4;
-  int stages = (227 * 1024 - 1024 - scratch - tail) / MK_STAGE_BYTES;
+  int stages = (227 * 1024 - scratch - tail) / MK_STAGE_BYTES;
   if (stages > MK_MAX_STAGES) stages = MK_MAX_STAGES;
   if (stages < 2) return fail(DN_EINVAL, "model too wide for the megakernel's shared-memory ring");
   p.n_stages = stages;
@@ -718,6 +718,11 @@ extern "C" int dn_enable_peer(int peer) {
 }
 extern "C" int dn_hop_send(void* dst_slot, const void* src, size_t bytes, uint32_t* dst_flag, uint32_t seq, dn_stream s) {
   if (!dst_slot || !src || !dst_flag) return fail(DN_EINVAL, "null argument");
+  if (bytes <= 65536 && (bytes % 16) == 0 && !((((uintptr_t)dst_slot) | ((uintptr_t)src)) & 15)) {
+    CK(launch(k_hop_send, dim3(1), dim3(512), 0, (cudaStream_t)s, false, (uint4*)dst_slot, (const uint4*)src,
+              (int)(bytes / 16), dst_flag, seq));
+    return DN_OK;
+  }
   CK(cudaMemcpyAsync(dst_slot, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
   CK(launch(k_flag_set, dim3(1), dim3(32), 0, (cudaStream_t)s, false, dst_flag, seq));
   return DN_OK;

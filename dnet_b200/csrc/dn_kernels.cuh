@@ -647,6 +647,16 @@ __global__ void k_flag_set(uint32_t* flag, uint32_t seq) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
   }
 }
+// decode hop: payload (<= 64 KiB) and flag in one launch -- peer stores over NVLink, then a
+// system-scope release of the sequence number.  No copy engine is involved, so a hop can never
+// queue behind an unrelated cudaMemcpy (copy-engine queues are shared across streams).
+__global__ void __launch_bounds__(512) k_hop_send(uint4* __restrict__ dst, const uint4* __restrict__ src, int n16,
+                                                  uint32_t* flag, uint32_t seq) {
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
 __global__ void k_flag_wait(const uint32_t* flag, uint32_t seq, unsigned long long timeout_ns, uint32_t* err) {
   if (threadIdx.x != 0) return;
   unsigned long long t0;

@@ -7,11 +7,11 @@
 //   * one CTA per SM (grid = #SMs), 9 warps: warp 8 is a PRODUCER that streams this CTA's
 //     share of every weight matrix of every layer through a shared-memory ring with TMA bulk
 //     copies (cp.async.bulk + mbarrier complete_tx): no registers are tied up by loads in
-//     flight, ~11 x 16 KB per SM are always outstanding, and because weights are immutable the
+//     flight, ~6 x 32 KB per SM are always outstanding, and because weights are immutable the
 //     producer never waits for a phase boundary -- HBM streams continuously across all the
 //     phases and layers of the step;
-//   * warps 0-7 are CONSUMERS: they wait on a stage's full-barrier, read the 32-row x 256-col
-//     bf16 tile from shared memory (each warp owns 4 rows of the tile, so there is no
+//   * warps 0-7 are CONSUMERS: they wait on a stage's full-barrier, read the 16-row x 1024-col
+//     bf16 tile from shared memory (each warp owns 2 rows of the tile, so there is no
 //     cross-warp reduction and no block barrier per row block), keep fp32 partial sums, and
 //     run the same fused epilogues as the per-op kernels (RoPE + paged-KV append, residual,
 //     SwiGLU, argmax/logsumexp);
@@ -27,10 +27,12 @@ namespace dn {
 constexpr int MK_CW = 8;                        // consumer warps
 constexpr int MK_CTHREADS = MK_CW * 32;         // 256
 constexpr int MK_THREADS = MK_CTHREADS + 32;    // + producer warp
-constexpr int MK_ROWS = 32;                     // rows per ring stage
-constexpr int MK_ROW_BYTES = 512;               // 256 bf16 columns per row per stage
-constexpr int MK_STAGE_BYTES = MK_ROWS * MK_ROW_BYTES;   // 16 KB
-constexpr int MK_MAX_STAGES = 12;
+constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
+constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
+constexpr int MK_STAGE_BYTES = MK_ROWS * MK_MAX_SEG * 2;   // 32 KB
+constexpr int MK_MAX_STAGES = 8;
+// r01 measurement: with 512-byte bulk copies the step ran at 2.2 TB/s (one TMA op per ~66
+// cycles per SM is the limit, not bytes), so a stage is 16 rows x 1024 columns = 16 ops of 2 KiB.
 constexpr unsigned long long MK_TIMEOUT_NS = 4000000000ull;  // bounded spins
 
 enum { MK_W_Q = 0, MK_W_K, MK_W_V, MK_W_O, MK_W_GATE, MK_W_UP, MK_W_DOWN, MK_W_LN1, MK_W_LN2, MK_W_QB, MK_W_KB, MK_W_VB, MK_W_N };
@@ -155,7 +157,7 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int&
 enum { PH_QKV = 0, PH_O = 1, PH_GU = 2, PH_DOWN = 3, PH_HEAD = 4 };
 
 struct MkPhase {
-  int K, nrows, align;
+  int K, nrows, align, seg;   // seg: columns per row per stage (largest of 1024/512/256 dividing K)
 };
 __device__ __forceinline__ MkPhase mk_phase(const MkParams& p, int ph) {
   MkPhase d;
@@ -166,6 +168,7 @@ __device__ __forceinline__ MkPhase mk_phase(const MkParams& p, int ph) {
     case PH_DOWN: d.K = p.FFN; d.nrows = p.H; d.align = 1; break;
     default: d.K = p.H; d.nrows = p.vocab; d.align = 1; break;
   }
+  d.seg = (d.K % 1024 == 0) ? 1024 : ((d.K % 512 == 0) ? 512 : 256);
   return d;
 }
 __device__ __forceinline__ const bf16* mk_row(const MkParams& p, const MkLayer& L, int ph, int vr, int K) {
@@ -208,17 +211,18 @@ __device__ __forceinline__ void mk_produce(const MkParams& p, const MkLayer& L, 
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
-  const int nchunks = d.K >> 8;
+  const int nseg = d.K / d.seg;
+  const uint32_t rowbytes = (uint32_t)d.seg * 2u;
   for (int rb = r0; rb < r1; rb += MK_ROWS) {
     const int nv = min(MK_ROWS, r1 - rb);
     const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
-    for (int c = 0; c < nchunks; ++c) {
+    for (int sg = 0; sg < nseg; ++sg) {
       mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
-      if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * MK_ROW_BYTES);
+      if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * rowbytes);
       __syncwarp();
       if (lane < nv)
-        tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + lane * MK_ROW_BYTES, src + (c << 8),
-                     MK_ROW_BYTES, &ring.full[ring.stage]);
+        tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes, src + (size_t)sg * d.seg,
+                     rowbytes, &ring.full[ring.stage]);
       ring.advance();
     }
   }
@@ -226,7 +230,8 @@ __device__ __forceinline__ void mk_produce(const MkParams& p, const MkLayer& L, 
 
 // ---------------------------------------------------------------------------------
 // consumer: one GEMV phase.  Epi is called by every lane with (vr, v, partner, valid); the
-// lanes with (lane & 7) == 0 are the row owners (4 rows per warp per block).
+// lanes 0 and 16 are the row owners (2 rows per warp per block); the partner row of a
+// RoPE / SwiGLU pair sits 16 lanes away.
 // ---------------------------------------------------------------------------------
 template <class Epi>
 __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ring, const bf16* xs, int cw, int lane,
@@ -234,23 +239,28 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ri
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
-  const int nchunks = d.K >> 8;
+  const int nseg = d.K / d.seg;
+  const int nch = d.seg >> 8;
+  const int rowbytes = d.seg * 2;
   for (int rb = r0; rb < r1; rb += MK_ROWS) {
     const int nv = min(MK_ROWS, r1 - rb);
-    const int myrows = min(4, max(0, nv - 4 * cw));
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < nchunks; ++c) {
+    const int myrows = min(2, max(0, nv - 2 * cw));
+    float acc[2] = {0.f, 0.f};
+    for (int sg = 0; sg < nseg; ++sg) {
       mbar_wait(&ring.full[ring.stage], ring.phase, p.err);
       if (myrows > 0) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(xs + (c << 8) + (lane << 3));
-        const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
-                             bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
-        const unsigned char* tile = ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (4 * cw) * MK_ROW_BYTES + lane * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < myrows) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(tile + j * MK_ROW_BYTES);
-            acc[j] = dot8(wv, xf, acc[j]);
+        const unsigned char* tile = ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)(2 * cw) * rowbytes + lane * 16;
+        const bf16* xseg = xs + (size_t)sg * d.seg + (lane << 3);
+#pragma unroll 4
+        for (int ch = 0; ch < nch; ++ch) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(xseg + (ch << 8));
+          const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
+                               bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
+          const uint4 w0 = *reinterpret_cast<const uint4*>(tile + (ch << 9));
+          acc[0] = dot8(w0, xf, acc[0]);
+          if (myrows > 1) {
+            const uint4 w1 = *reinterpret_cast<const uint4*>(tile + rowbytes + (ch << 9));
+            acc[1] = dot8(w1, xf, acc[1]);
           }
         }
       }
@@ -258,26 +268,16 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ri
       if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
       ring.advance();
     }
-    // 4 values per lane -> lane group g = lane>>3 owns row 4*cw + (bit4*2 + bit3)
-    {
-      const bool up = (lane & 16) != 0;
-      const float k0 = up ? acc[2] : acc[0], k1 = up ? acc[3] : acc[1];
-      const float s0 = up ? acc[0] : acc[2], s1 = up ? acc[1] : acc[3];
-      acc[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
-      acc[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-    }
-    {
-      const bool up = (lane & 8) != 0;
-      const float k = up ? acc[1] : acc[0], s = up ? acc[0] : acc[1];
-      acc[0] = k + __shfl_xor_sync(0xffffffffu, s, 8);
-    }
-    float v = acc[0];
+    // 2 values per lane -> lanes 0-15 end with row 2*cw, lanes 16-31 with row 2*cw + 1
+    const bool up = (lane & 16) != 0;
+    const float keep = up ? acc[1] : acc[0], send = up ? acc[0] : acc[1];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
-    const int j = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-    const int r_local = 4 * cw + j;
-    epi(rb + r_local, v, r_local < nv && (lane & 7) == 0);
+    const int r_local = 2 * cw + ((lane >> 4) & 1);
+    epi(rb + r_local, v, r_local < nv && (lane & 15) == 0);
   }
 }
 
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const bf16* bias = L.w[kind == 0 ? MK_W_QB : (kind == 1 ? MK_W_KB : MK_W_VB)];
       if (owner && bias != nullptr) v += __bfloat162float(bias[hrow * HD + dim]);
       const float y = bf16r(v);
-      const float yp = __shfl_xor_sync(0xffffffffu, y, 8);
+      const float yp = __shfl_xor_sync(0xffffffffu, y, 16);
       if (!owner) return;
       float o = y;
       if (kind != 2) {
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
     mk_consume(p, PH_GU, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
       const float y = bf16r(v);
-      const float u = __shfl_xor_sync(0xffffffffu, y, 8);
+      const float u = __shfl_xor_sync(0xffffffffu, y, 16);
       if (!owner || (vr & 1)) return;
       const float s = bf16r(1.0f / (1.0f + expf(-y)));
       const float a = bf16r(__fmul_rn(y, s));

@@ -44,18 +44,21 @@ class FitInMemoryPolicy(ComputePolicy):
 
     # -- CUDA-graph fast path for single-token messages ----------------------------------
     def _graph_step(self, ns, x, is_tokens: bool, run: list[int], fused_head: bool) -> None:
-        """Replay (capturing on first use) [embed] + window + [norm/head/argmax] + advance."""
+        """Replay (capturing on first use) [embed] + window + [norm/head/argmax] + advance.
+        The KV offset advances once per token: on the visit that computes the shard's last
+        local layer (with k>1 rounds a shard is visited k times per token, api/utils.py:62-131)."""
         rt = self.runtime
         lib = _cabi.load()
         s = rt.compute_stream_ptr
+        adv = 1 if run[-1] == rt._assigned_sorted[-1] else 0
         if rt.use_megakernel:
             # one persistent cooperative kernel for the whole step (dn_megakernel.cuh)
             arr = (C.c_int32 * len(run))(*run)
             _cabi.check(lib.dn_shard_step(rt.model._h, arr, len(run), x.data_ptr(), ns.kv._h, int(is_tokens),
                                           int(fused_head), ns.result_token_ptr if fused_head else None,
-                                          ns.result_logprob_ptr if fused_head else None, None, 1, s))
+                                          ns.result_logprob_ptr if fused_head else None, None, adv, s))
             return
-        key = (run[0], is_tokens, fused_head)
+        key = (run[0], is_tokens, fused_head, adv)
         g = ns.graphs.get(key)
         if g is None:
             rt.compute_stream.synchronize()
@@ -69,14 +72,16 @@ class FitInMemoryPolicy(ComputePolicy):
                 if fused_head:
                     _cabi.check(lib.dn_head_sample_greedy(rt.model._h, x.data_ptr(), 1, ns.kv._h,
                                                           ns.result_token_ptr, ns.result_logprob_ptr, s))
-                _cabi.check(lib.dn_kv_advance(ns.kv._h, 1, s))
+                if adv:
+                    _cabi.check(lib.dn_kv_advance(ns.kv._h, 1, s))
             finally:
                 rc = lib.dn_graph_end(s, C.byref(gp))
             _cabi.check(rc)
             g = gp.value
             ns.graphs[key] = g
         _cabi.check(lib.dn_graph_launch(g, s))
-        ns.kv.note_advance(1)
+        if adv:
+            ns.kv.note_advance(1)
 
     def process(self, msg: ActivationMessage) -> None:
         rt = self.runtime
@@ -151,7 +156,8 @@ class FitInMemoryPolicy(ComputePolicy):
                         rt.model.window_forward(window_layers, x, ns.kv, rt.compute_stream_ptr)
                         for lid in window_layers:
                             self.weight_cache.decrease_reference(lid)
-                    ns.kv.advance(T, rt.compute_stream_ptr)
+                    if last_layer == rt._assigned_sorted[-1]:
+                        ns.kv.advance(T, rt.compute_stream_ptr)
                 if is_end and final is None:
                     try:
                         final = cc.sample_end_shard(rt, msg, ns, x)

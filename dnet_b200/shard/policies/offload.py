@@ -207,7 +207,8 @@ class OffloadPolicy(ComputePolicy):
                         continue
                     break
 
-                ns.kv.advance(T, rt.compute_stream_ptr)
+                if last_layer == rt._assigned_sorted[-1]:   # once per token even with k>1 rounds
+                    ns.kv.advance(T, rt.compute_stream_ptr)
                 final = None
                 if last_layer + 1 >= rt.model_metadata.num_layers:
                     try:

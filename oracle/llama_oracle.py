@@ -160,7 +160,11 @@ class LlamaOracle:
             if bias is not None and bias in self.w:
                 y = y + self.w[bias].to(torch.float64)
             return self.T(y.to(torch.float32) if self.dtype == torch.float32 else y)
-        if self.exact_linear or self.dtype == torch.float32:
+        rows = x.shape[0] if x.dim() > 1 else 1
+        if self.exact_linear or self.dtype == torch.float32 or rows > 1:
+            # fp32 accumulate of exact bf16 products.  (oneDNN's bf16 GEMM is used only for
+            # single-row GEMV, where it was checked to be one correctly rounded fp32 sum; for
+            # M > 1 it rounds differently, so prefill always takes this path.)
             y = x.to(torch.float32) @ W.to(torch.float32).T
         else:
             # oneDNN/ATen bf16 GEMM: fp32 accumulate, single rounding to bf16

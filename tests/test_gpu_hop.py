@@ -13,18 +13,32 @@ def test_hop_send_wait_and_bounded_timeout(cuda_lib):
     lib = cuda_lib
     slot, flags = C.c_void_p(), C.c_void_p()
     _cabi.check(lib.dn_hop_alloc(8192, C.byref(slot)))
-    _cabi.check(lib.dn_hop_alloc(64, C.byref(flags)))
+    _cabi.check(lib.dn_hop_alloc(256, C.byref(flags)))
     s_tx, s_rx = torch.cuda.Stream(), torch.cuda.Stream()
     src = torch.arange(4096, dtype=torch.int16, device="cuda")
     dst_view = torch.empty(4096, dtype=torch.int16).pin_memory()
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()          # tensors above were made on torch's stream
-    # receiver first: waits on seq 1, then copies the slot out
+    # receiver first: the wait kernel spins on seq 1 while the sender's hop kernel runs on another stream
     _cabi.check(lib.dn_hop_wait(flags.value, 1, 2000, err.data_ptr(), s_rx.cuda_stream))
-    _cabi.check(lib.dn_memcpy_d2h(dst_view.data_ptr(), slot.value, 8192, s_rx.cuda_stream))
     _cabi.check(lib.dn_hop_send(slot.value, src.data_ptr(), 8192, flags.value, 1, s_tx.cuda_stream))
+    # (enqueued after the send: a copy queued behind the spinning wait would otherwise share a
+    #  copy-engine queue with any cudaMemcpy-based send -- the reason dn_hop_send is a kernel)
+    _cabi.check(lib.dn_memcpy_d2h(dst_view.data_ptr(), slot.value, 8192, s_rx.cuda_stream))
     s_rx.synchronize()
     assert torch.equal(dst_view, src.cpu()) and int(err.item()) == 0
+    # large payloads take the cudaMemcpyAsync + flag path
+    big = torch.arange(1 << 20, dtype=torch.int16, device="cuda")
+    bslot = C.c_void_p()
+    _cabi.check(lib.dn_hop_alloc(2 << 20, C.byref(bslot)))
+    torch.cuda.synchronize()
+    _cabi.check(lib.dn_hop_send(bslot.value, big.data_ptr(), 2 << 20, flags.value + 64, 7, s_tx.cuda_stream))
+    _cabi.check(lib.dn_hop_wait(flags.value + 64, 7, 2000, err.data_ptr(), s_rx.cuda_stream))
+    bdst = torch.empty(1 << 20, dtype=torch.int16).pin_memory()
+    _cabi.check(lib.dn_memcpy_d2h(bdst.data_ptr(), bslot.value, 2 << 20, s_rx.cuda_stream))
+    s_rx.synchronize()
+    assert torch.equal(bdst, big.cpu()) and int(err.item()) == 0
+    _cabi.check(lib.dn_hop_free(bslot.value))
     # a flag that never arrives: the wait kernel gives up after the timeout and reports it
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(s_rx)
