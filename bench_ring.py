@@ -56,6 +56,8 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                                              window_size=len(mine), residency_size=len(mine), kv_bits="fp16"))
     lib.dn_set_option(b"pdl", 1 if args.pdl else 0)
     lib.dn_set_option(b"l2_prefetch_kb", args.l2_prefetch_kb)
+    if args.pf_depth >= 0:
+        lib.dn_set_option(b"pf_depth", args.pf_depth)
     pol, model = rt.policy, rt.model
     s = rt.compute_stream_ptr
     stream = rt.compute_stream

@@ -38,6 +38,7 @@ static int fail(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
+static int g_pf_depth = 10;   // megakernel producer: L2 prefetch look-ahead in 32 KB ring stages
 static int g_sms = 0;
 static int g_device = -1;
 static bool g_capturing = false;
@@ -163,6 +164,15 @@ static cudaError_t init_kernel_attrs() {
   SETA(1, OpGateUp) SETA(2, OpGateUp) SETA(4, OpGateUp)
   SETA(1, OpHead)
 #undef SETA
+  // CUDA loads kernels lazily; loading can need a context-wide sync, so the first launch of a
+  // kernel issued while k_flag_wait is spinning would deadlock until its timeout.  Touch every
+  // kernel once here.
+  cudaFuncAttributes fa;
+#define PRE(k) if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
+  PRE(k_hop_send) PRE(k_flag_set) PRE(k_flag_wait) PRE(k_embed) PRE(k_advance) PRE(k_set_state)
+  PRE(k_attn<1>) PRE(k_attn<2>) PRE(k_attn<4>) PRE(k_attn<5>) PRE(k_attn<7>) PRE(k_attn<8>)
+  PRE(k_shard_step<1>) PRE(k_shard_step<2>) PRE(k_shard_step<4>) PRE(k_shard_step<5>) PRE(k_shard_step<7>) PRE(k_shard_step<8>)
+#undef PRE
   return cudaSuccess;
 }
 
@@ -191,6 +201,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!key) return fail(DN_EINVAL, "null option key");
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
+  if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
   return fail(DN_EINVAL, "unknown option '%s'", key);
 }
 
@@ -600,7 +611,8 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   p.norm_w = m->norm; p.head_w = m->head; p.logits_bf16 = m->logits_bf16; p.logits_f32 = logits_f32_out;
   p.head_part = m->head_part; p.head_ticket = m->mk_sync + 3;
   p.token_out = token_out; p.logprob_out = logprob_out; p.do_head = do_head ? 1 : 0; p.advance = advance ? 1 : 0;
-  p.bar_count = m->mk_sync; p.bar_gen = m->mk_sync + 1; p.err = m->mk_sync + 2;
+  p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
+  p.pf_depth = g_pf_depth;
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
   const int attn_bytes = 2 * PAGE * HD * 2 + 8 * 32 * 4 + 64;

@@ -64,8 +64,9 @@ struct MkParams {
   int32_t* token_out;
   float* logprob_out;
   int do_head, advance;
-  unsigned int *bar_count, *bar_gen, *err;
+  unsigned int *bar_count, *bar_epoch, *err;   // monotonic arrival counter, its value at launch start
   int n_stages;
+  int pf_depth;           // L2 prefetch look-ahead of the producer, in ring stages
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
 };
 
@@ -117,6 +118,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, ui
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// bulk L2 prefetch: pulls the bytes toward L2 without occupying a ring stage
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MK_CTHREADS) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   uint32_t v;
@@ -125,20 +130,19 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
 }
 
 // grid barrier among the consumer warps of all CTAs (all CTAs are co-resident: grid = #SMs,
-// one CTA per SM, launched cooperatively)
-__device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int& gen) {
+// one CTA per SM, launched cooperatively).  One monotonic counter: barrier k of this launch is
+// passed when the counter reaches base + (k+1)*grid, where base is the counter value at launch
+// start (published by the previous launch in bar_epoch) -- one atomic round trip + one poll.
+__device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int base, unsigned int& k) {
   cbar_sync();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int arrived = atomicAdd(p.bar_count, 1u);
-    if (arrived == gridDim.x - 1) {
-      atomicExch(p.bar_count, 0u);
-      __threadfence();
-      atomicAdd(p.bar_gen, 1u);
-    } else {
+    atomicAdd(p.bar_count, 1u);
+    const unsigned int target = base + (k + 1u) * gridDim.x;
+    if ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
       const unsigned long long t0 = gtimer();
       unsigned it = 0;
-      while (ld_acquire_gpu(p.bar_gen) == gen) {
+      while ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
         if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) {
           atomicExch(p.err, 3u);
           break;
@@ -147,7 +151,7 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int&
     }
     __threadfence();
   }
-  gen += 1;
+  k += 1u;
   cbar_sync();
 }
 
@@ -205,26 +209,79 @@ struct MkRing {
 };
 
 // ---------------------------------------------------------------------------------
-// producer: stream one GEMV phase of this CTA through the ring
+// producer: an iterator over this CTA's ring stages in execution order
+//   layers x {QKV, O, GATE/UP, DOWN} x row blocks x K segments, then the head phase.
+// Two cursors walk the same sequence: the load cursor feeds the ring with TMA bulk copies,
+// the prefetch cursor runs pf_depth stages ahead issuing L2 bulk prefetches, so HBM keeps
+// streaming into L2 while the ring is full (consumers inside a barrier / attention phase) and
+// the ring then refills at L2 speed.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void mk_produce(const MkParams& p, const MkLayer& L, int ph, MkRing& ring, int lane) {
-  const MkPhase d = mk_phase(p, ph);
-  int r0, r1;
-  mk_range(d, r0, r1);
-  const int nseg = d.K / d.seg;
-  const uint32_t rowbytes = (uint32_t)d.seg * 2u;
-  for (int rb = r0; rb < r1; rb += MK_ROWS) {
-    const int nv = min(MK_ROWS, r1 - rb);
-    const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
-    for (int sg = 0; sg < nseg; ++sg) {
-      mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
-      if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * rowbytes);
-      __syncwarp();
-      if (lane < nv)
-        tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes, src + (size_t)sg * d.seg,
-                     rowbytes, &ring.full[ring.stage]);
-      ring.advance();
+struct MkIter {
+  int li, ph;            // layer, phase
+  int rb, r1, sg, nseg, seg, K, nv;
+  const bf16* src;       // this lane's row (rb + lane) or nullptr
+  bool done;
+};
+__device__ __forceinline__ void mk_iter_rows(const MkParams& p, MkIter& it, int lane) {
+  it.nv = min(MK_ROWS, it.r1 - it.rb);
+  const MkLayer& L = p.layers[it.ph == PH_HEAD ? 0 : it.li];
+  it.src = (lane < it.nv) ? mk_row(p, L, it.ph, it.rb + lane, it.K) : nullptr;
+  it.sg = 0;
+}
+// position the iterator at the first non-empty phase at or after (li, ph)
+__device__ __forceinline__ void mk_iter_seek(const MkParams& p, MkIter& it, int lane) {
+  for (;;) {
+    if (it.li >= p.n_layers) {
+      if (!p.do_head || it.ph > PH_HEAD) { it.done = true; return; }
+      it.ph = PH_HEAD;
     }
+    const MkPhase d = mk_phase(p, it.ph);
+    int r0;
+    mk_range(d, r0, it.r1);
+    if (r0 < it.r1) {
+      it.K = d.K; it.seg = d.seg; it.nseg = d.K / d.seg; it.rb = r0;
+      mk_iter_rows(p, it, lane);
+      return;
+    }
+    if (it.ph == PH_HEAD) { it.done = true; return; }
+    if (++it.ph > PH_DOWN) { it.ph = PH_QKV; ++it.li; }
+  }
+}
+__device__ __forceinline__ void mk_iter_begin(const MkParams& p, MkIter& it, int lane) {
+  it.li = 0; it.ph = PH_QKV; it.done = false;
+  if (p.n_layers == 0) it.ph = PH_HEAD;
+  mk_iter_seek(p, it, lane);
+}
+__device__ __forceinline__ void mk_iter_next(const MkParams& p, MkIter& it, int lane) {
+  if (++it.sg < it.nseg) return;
+  it.rb += MK_ROWS;
+  if (it.rb < it.r1) { mk_iter_rows(p, it, lane); return; }
+  if (it.ph == PH_HEAD) { it.done = true; return; }
+  if (++it.ph > PH_DOWN) { it.ph = PH_QKV; ++it.li; }
+  mk_iter_seek(p, it, lane);
+}
+
+__device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int lane) {
+  MkIter ld, pf;
+  mk_iter_begin(p, ld, lane);
+  mk_iter_begin(p, pf, lane);
+  int ahead = 0;
+  while (!ld.done) {
+    while (ahead < p.pf_depth && !pf.done) {
+      if (pf.src != nullptr) tma_prefetch_l2(pf.src + (size_t)pf.sg * pf.seg, (uint32_t)pf.seg * 2u);
+      mk_iter_next(p, pf, lane);
+      ++ahead;
+    }
+    const uint32_t rowbytes = (uint32_t)ld.seg * 2u;
+    mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
+    if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)ld.nv * rowbytes);
+    __syncwarp();
+    if (ld.src != nullptr)
+      tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes,
+                   ld.src + (size_t)ld.sg * ld.seg, rowbytes, &ring.full[ring.stage]);
+    ring.advance();
+    mk_iter_next(p, ld, lane);
+    --ahead;
   }
 }
 
@@ -461,25 +518,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
 
   if (warp == MK_CW) {
     // ===== PRODUCER: never waits for activations; runs ahead across phases and layers =====
-    for (int li = 0; li < p.n_layers; ++li) {
-      const MkLayer L = p.layers[li];
-      mk_produce(p, L, PH_QKV, ring, lane);
-      mk_produce(p, L, PH_O, ring, lane);
-      mk_produce(p, L, PH_GU, ring, lane);
-      mk_produce(p, L, PH_DOWN, ring, lane);
-    }
-    if (p.do_head) {
-      MkLayer dummy = p.layers[0];
-      mk_produce(p, dummy, PH_HEAD, ring, lane);
-    }
+    mk_producer(p, ring, lane);
     return;
   }
 
   // ===== CONSUMERS =====
   const int cw = warp;
   bf16* xs = reinterpret_cast<bf16*>(scratch);
-  unsigned int gen = 0;
-  if (threadIdx.x == 0) gen = ld_acquire_gpu(p.bar_gen);
+  unsigned int bar_k = 0;
+  const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
   const int pos = p.st->pos;
   const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(p.st->token, 0), p.vocab - 1) * p.H : p.x_in;
 
@@ -517,11 +564,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
         L.kv_pool[off] = __float2bfloat16_rn(o);
       }
     });
-    mk_grid_barrier(p, gen);
+    mk_grid_barrier(p, bar_base, bar_k);
 
     // ---- P2: paged-KV attention (split over pages, last-CTA merge)
     mk_attention<G>(p, L, scratch, cw, lane);
-    mk_grid_barrier(p, gen);
+    mk_grid_barrier(p, bar_base, bar_k);
 
     // ---- P3: o_proj + residual
     mk_stage_copy(xs, p.attn, p.n_heads * HD);
@@ -531,7 +578,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const unsigned short xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
       p.hbuf[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(xb_)), o));
     });
-    mk_grid_barrier(p, gen);
+    mk_grid_barrier(p, bar_base, bar_k);
 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
@@ -543,7 +590,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const float a = bf16r(__fmul_rn(y, s));
       p.act[vr >> 1] = __float2bfloat16_rn(__fmul_rn(a, u));
     });
-    mk_grid_barrier(p, gen);
+    mk_grid_barrier(p, bar_base, bar_k);
 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
@@ -553,7 +600,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const unsigned short hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
       nxt[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(hb)), o));
     });
-    mk_grid_barrier(p, gen);
+    mk_grid_barrier(p, bar_base, bar_k);
     cur = nxt;
   }
 
@@ -622,7 +669,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       }
     }
   }
-  if (p.advance && blockIdx.x == 0 && threadIdx.x == 0) p.st->pos = pos + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.advance) p.st->pos = pos + 1;
+    *p.bar_epoch = bar_base + bar_k * gridDim.x;   // every CTA passed bar_k barriers; next launch starts here
+  }
 }
 
 }  // namespace dn
