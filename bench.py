@@ -242,6 +242,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     rt.use_megakernel = bool(args.megakernel)
     if args.pf_depth >= 0:
         lib.dn_set_option(b"pf_depth", args.pf_depth)
+    lib.dn_set_option(b"mk_flags", args.mk_flags)
     pol = rt.policy
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(0, cfg["vocab_size"], (PROMPT_LEN,), generator=g).tolist()
@@ -400,6 +401,7 @@ def main():
     ap.add_argument("--megakernel", type=int, default=int(os.environ.get("DNET_COMPUTE_MEGAKERNEL", "1")))
     ap.add_argument("--l2-prefetch-kb", type=int, default=64)
     ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--mk-flags", type=int, default=0)
     ap.add_argument("--pf-depth", type=int, default=-1, help="megakernel L2 prefetch look-ahead (ring stages); -1 = library default")
     ap.add_argument("--in-flight", type=int, default=0, help="sequences in flight at N>1 (default N)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -38,6 +38,7 @@ static int fail(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
+static int g_mk_flags = 0;
 static int g_pf_depth = 10;   // megakernel producer: L2 prefetch look-ahead in 32 KB ring stages
 static int g_sms = 0;
 static int g_device = -1;
@@ -201,6 +202,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!key) return fail(DN_EINVAL, "null option key");
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
+  if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
   if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
   return fail(DN_EINVAL, "unknown option '%s'", key);
 }
@@ -613,6 +615,8 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   p.token_out = token_out; p.logprob_out = logprob_out; p.do_head = do_head ? 1 : 0; p.advance = advance ? 1 : 0;
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
+  p.flags = g_mk_flags;
+  p.bar_gen = m->mk_sync + 4;
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
   const int attn_bytes = 2 * PAGE * HD * 2 + 8 * 32 * 4 + 64;

@@ -26,7 +26,8 @@ namespace dn {
 
 constexpr int MK_CW = 8;                        // consumer warps
 constexpr int MK_CTHREADS = MK_CW * 32;         // 256
-constexpr int MK_THREADS = MK_CTHREADS + 32;    // + producer warp
+constexpr int MK_PW = 2;                        // producer warps (alternate ring stages)
+constexpr int MK_THREADS = MK_CTHREADS + (MK_PW + 1) * 32;   // + producers + L2 prefetch warp
 constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
 constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
 constexpr int MK_STAGE_BYTES = MK_ROWS * MK_MAX_SEG * 2;   // 32 KB
@@ -67,6 +68,8 @@ struct MkParams {
   unsigned int *bar_count, *bar_epoch, *err;   // monotonic arrival counter, its value at launch start
   int n_stages;
   int pf_depth;           // L2 prefetch look-ahead of the producer, in ring stages
+  int flags;              // bit0: two-word (count + generation) grid barrier; bit1: nested-loop producer without L2 prefetch
+  unsigned int* bar_gen;
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
 };
 
@@ -135,7 +138,24 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
 // start (published by the previous launch in bar_epoch) -- one atomic round trip + one poll.
 __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int base, unsigned int& k) {
   cbar_sync();
-  if (threadIdx.x == 0) {
+  if ((p.flags & 1) && threadIdx.x == 0) {
+    // two-word variant: the last arriver resets the count and bumps a generation word
+    const unsigned int gen = ld_acquire_gpu(p.bar_gen);
+    __threadfence();
+    const unsigned int arrived = atomicAdd(p.bar_count, 1u);
+    if (arrived == gridDim.x - 1) {
+      atomicExch(p.bar_count, 0u);
+      __threadfence();
+      atomicAdd(p.bar_gen, 1u);
+    } else {
+      const unsigned long long t0 = gtimer();
+      unsigned it = 0;
+      while (ld_acquire_gpu(p.bar_gen) == gen) {
+        if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
+      }
+    }
+    __threadfence();
+  } else if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(p.bar_count, 1u);
     const unsigned int target = base + (k + 1u) * gridDim.x;
@@ -209,79 +229,92 @@ struct MkRing {
 };
 
 // ---------------------------------------------------------------------------------
-// producer: an iterator over this CTA's ring stages in execution order
-//   layers x {QKV, O, GATE/UP, DOWN} x row blocks x K segments, then the head phase.
-// Two cursors walk the same sequence: the load cursor feeds the ring with TMA bulk copies,
-// the prefetch cursor runs pf_depth stages ahead issuing L2 bulk prefetches, so HBM keeps
-// streaming into L2 while the ring is full (consumers inside a barrier / attention phase) and
-// the ring then refills at L2 speed.
+// producers: MK_PW warps walk this CTA's ring stages in execution order (layers x {QKV, O,
+// GATE/UP, DOWN} x row blocks x K segments, then the head); warp `which` feeds the stages
+// whose running index has that parity, so two TMA issue loops run concurrently (one warp
+// issuing sixteen 2 KiB bulk copies per stage sustains ~56 GB/s per SM -- enough for the HBM
+// share but not for refilling the ring from L2 after a stall).
 // ---------------------------------------------------------------------------------
-struct MkIter {
-  int li, ph;            // layer, phase
-  int rb, r1, sg, nseg, seg, K, nv;
-  const bf16* src;       // this lane's row (rb + lane) or nullptr
-  bool done;
-};
-__device__ __forceinline__ void mk_iter_rows(const MkParams& p, MkIter& it, int lane) {
-  it.nv = min(MK_ROWS, it.r1 - it.rb);
-  const MkLayer& L = p.layers[it.ph == PH_HEAD ? 0 : it.li];
-  it.src = (lane < it.nv) ? mk_row(p, L, it.ph, it.rb + lane, it.K) : nullptr;
-  it.sg = 0;
-}
-// position the iterator at the first non-empty phase at or after (li, ph)
-__device__ __forceinline__ void mk_iter_seek(const MkParams& p, MkIter& it, int lane) {
-  for (;;) {
-    if (it.li >= p.n_layers) {
-      if (!p.do_head || it.ph > PH_HEAD) { it.done = true; return; }
-      it.ph = PH_HEAD;
+__device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLayer& L, int ph, MkRing& ring, int lane,
+                                                 int which, unsigned int& idx) {
+  const MkPhase d = mk_phase(p, ph);
+  int r0, r1;
+  mk_range(d, r0, r1);
+  const int nseg = d.K / d.seg;
+  const uint32_t rowbytes = (uint32_t)d.seg * 2u;
+  for (int rb = r0; rb < r1; rb += MK_ROWS) {
+    const int nv = min(MK_ROWS, r1 - rb);
+    const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
+    for (int sg = 0; sg < nseg; ++sg) {
+      if ((int)(idx % MK_PW) == which) {
+        mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
+        if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * rowbytes);
+        __syncwarp();
+        if (lane < nv)
+          tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes,
+                       src + (size_t)sg * d.seg, rowbytes, &ring.full[ring.stage]);
+      }
+      ++idx;
+      ring.advance();
     }
-    const MkPhase d = mk_phase(p, it.ph);
-    int r0;
-    mk_range(d, r0, it.r1);
-    if (r0 < it.r1) {
-      it.K = d.K; it.seg = d.seg; it.nseg = d.K / d.seg; it.rb = r0;
-      mk_iter_rows(p, it, lane);
-      return;
-    }
-    if (it.ph == PH_HEAD) { it.done = true; return; }
-    if (++it.ph > PH_DOWN) { it.ph = PH_QKV; ++it.li; }
   }
 }
-__device__ __forceinline__ void mk_iter_begin(const MkParams& p, MkIter& it, int lane) {
-  it.li = 0; it.ph = PH_QKV; it.done = false;
-  if (p.n_layers == 0) it.ph = PH_HEAD;
-  mk_iter_seek(p, it, lane);
-}
-__device__ __forceinline__ void mk_iter_next(const MkParams& p, MkIter& it, int lane) {
-  if (++it.sg < it.nseg) return;
-  it.rb += MK_ROWS;
-  if (it.rb < it.r1) { mk_iter_rows(p, it, lane); return; }
-  if (it.ph == PH_HEAD) { it.done = true; return; }
-  if (++it.ph > PH_DOWN) { it.ph = PH_QKV; ++it.li; }
-  mk_iter_seek(p, it, lane);
+__device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int lane, int which) {
+  unsigned int idx = 0;
+  for (int li = 0; li < p.n_layers; ++li) {
+    const MkLayer L = p.layers[li];
+    mk_produce_phase(p, L, PH_QKV, ring, lane, which, idx);
+    mk_produce_phase(p, L, PH_O, ring, lane, which, idx);
+    mk_produce_phase(p, L, PH_GU, ring, lane, which, idx);
+    mk_produce_phase(p, L, PH_DOWN, ring, lane, which, idx);
+  }
+  if (p.do_head) {
+    const MkLayer L0 = p.layers[0];
+    mk_produce_phase(p, L0, PH_HEAD, ring, lane, which, idx);
+  }
 }
 
-__device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int lane) {
-  MkIter ld, pf;
-  mk_iter_begin(p, ld, lane);
-  mk_iter_begin(p, pf, lane);
-  int ahead = 0;
-  while (!ld.done) {
-    while (ahead < p.pf_depth && !pf.done) {
-      if (pf.src != nullptr) tma_prefetch_l2(pf.src + (size_t)pf.sg * pf.seg, (uint32_t)pf.seg * 2u);
-      mk_iter_next(p, pf, lane);
-      ++ahead;
+// L2 prefetch warp: walks the same sequence `limit` stages ahead of consumption and issues bulk
+// L2 prefetches, so HBM keeps streaming into L2 while the ring is full (consumers inside a grid
+// barrier / staging / attention) and the ring then refills at L2 speed.
+__device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLayer& L, int ph, int lane, unsigned int& n,
+                                                  volatile unsigned int* consumed, unsigned int limit, bool& alive) {
+  const MkPhase d = mk_phase(p, ph);
+  int r0, r1;
+  mk_range(d, r0, r1);
+  const int nseg = d.K / d.seg;
+  const uint32_t rowbytes = (uint32_t)d.seg * 2u;
+  for (int rb = r0; rb < r1 && alive; rb += MK_ROWS) {
+    const int nv = min(MK_ROWS, r1 - rb);
+    const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
+    for (int sg = 0; sg < nseg; ++sg) {
+      if ((int)(n - *consumed) > (int)limit) {
+        const unsigned long long t0 = gtimer();
+        while ((int)(n - *consumed) > (int)limit) {
+          __nanosleep(64);
+          if (gtimer() - t0 > MK_TIMEOUT_NS) { alive = false; return; }
+        }
+      }
+      if (src != nullptr) tma_prefetch_l2(src + (size_t)sg * d.seg, rowbytes);
+      ++n;
     }
-    const uint32_t rowbytes = (uint32_t)ld.seg * 2u;
-    mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
-    if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)ld.nv * rowbytes);
-    __syncwarp();
-    if (ld.src != nullptr)
-      tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes,
-                   ld.src + (size_t)ld.sg * ld.seg, rowbytes, &ring.full[ring.stage]);
-    ring.advance();
-    mk_iter_next(p, ld, lane);
-    --ahead;
+  }
+}
+__device__ __forceinline__ void mk_prefetcher(const MkParams& p, int lane, volatile unsigned int* consumed) {
+  if (p.pf_depth <= 0) return;
+  unsigned int n = 0;
+  bool alive = true;
+  const unsigned int limit = (unsigned int)(p.pf_depth + p.n_stages);
+  for (int li = 0; li < p.n_layers && alive; ++li) {
+    const MkLayer L = p.layers[li];
+    mk_prefetch_phase(p, L, PH_QKV, lane, n, consumed, limit, alive);
+    mk_prefetch_phase(p, L, PH_O, lane, n, consumed, limit, alive);
+    mk_prefetch_phase(p, L, PH_GU, lane, n, consumed, limit, alive);
+    mk_prefetch_phase(p, L, PH_DOWN, lane, n, consumed, limit, alive);
+  }
+  if (p.do_head && alive) {
+    const MkLayer L0 = p.layers[0];
+    mk_prefetch_phase(p, L0, PH_HEAD, lane, n, consumed, limit, alive);
   }
 }
 
@@ -292,7 +325,7 @@ __device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int
 // ---------------------------------------------------------------------------------
 template <class Epi>
 __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ring, const bf16* xs, int cw, int lane,
-                                           Epi epi) {
+                                           volatile unsigned int* consumed, unsigned int& ncons, Epi epi) {
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
@@ -323,6 +356,8 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ri
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
+      ++ncons;
+      if (threadIdx.x == 0) *consumed = ncons;      // progress signal for the L2 prefetch warp
       ring.advance();
     }
     // 2 values per lane -> lanes 0-15 end with row 2*cw, lanes 16-31 with row 2*cw + 1
@@ -454,29 +489,27 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
     *reinterpret_cast<float4*>(pp + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
     if (lane == 0) { pp[128] = m; pp[129] = l; }
   }
-  __threadfence();
-  cbar_sync();
-  if (threadIdx.x == 0) {
-    const unsigned int old = atomicAdd(&p.tickets[kvh], 1u);
-    *s_last = (old == (unsigned)nact - 1) ? 1 : 0;
-  }
-  cbar_sync();
-  if (!*s_last) return;
-  __threadfence();
-  if (cw < G) {
+}
+
+// o_proj staging = merge of the attention splits (fixed order -> deterministic) straight into the
+// shared activation vector: every CTA does it redundantly from L2 (nact x 132 floats per head),
+// which removes the ticket + last-CTA merge + one more round trip from the critical path.
+__device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p) {
+  const int kv_len = p.st->pos + 1;
+  const int npages = (kv_len + PAGE - 1) / PAGE;
+  const int nact = min(p.nsplit, npages);
+  for (int gidx = threadIdx.x; gidx < p.n_heads * 32; gidx += MK_CTHREADS) {
+    const int head = gidx >> 5, l4 = gidx & 31;
     const float* hp = p.part + ((size_t)head * p.nsplit) * PART_STRIDE;
-    // lane s2 fetches split s2's (m, l) -> one round trip instead of nsplit dependent ones
-    const float ms = (lane < nact) ? __ldcg(hp + (size_t)lane * PART_STRIDE + 128) : -INFINITY;
-    const float ls = (lane < nact) ? __ldcg(hp + (size_t)lane * PART_STRIDE + 129) : 0.f;
-    const float M = warp_max(ms);
-    const float wgt = (ms == -INFINITY) ? 0.f : exp2f((ms - M) * LOG2E);
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(hp + (size_t)s2 * PART_STRIDE + 128));
     float Lsum = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s2 = 0; s2 < nact; ++s2) {               // fixed order -> deterministic
-      const float w2 = __shfl_sync(0xffffffffu, wgt, s2);
-      const float l2 = __shfl_sync(0xffffffffu, ls, s2);
-      if (w2 == 0.f) continue;
-      Lsum = fmaf(l2, w2, Lsum);
-      const float4 ov = __ldcg(reinterpret_cast<const float4*>(hp + (size_t)s2 * PART_STRIDE + lane * 4));
+    for (int s2 = 0; s2 < nact; ++s2) {
+      const float ms = __ldcg(hp + (size_t)s2 * PART_STRIDE + 128);
+      if (ms == -INFINITY) continue;
+      const float w2 = exp2f((ms - M) * LOG2E);
+      Lsum = fmaf(__ldcg(hp + (size_t)s2 * PART_STRIDE + 129), w2, Lsum);
+      const float4 ov = __ldcg(reinterpret_cast<const float4*>(hp + (size_t)s2 * PART_STRIDE + l4 * 4));
       acc[0] = fmaf(ov.x, w2, acc[0]); acc[1] = fmaf(ov.y, w2, acc[1]);
       acc[2] = fmaf(ov.z, w2, acc[2]); acc[3] = fmaf(ov.w, w2, acc[3]);
     }
@@ -484,9 +517,9 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
     __align__(8) bf16 ob[4];
 #pragma unroll
     for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(acc[dd] * invL);
-    *reinterpret_cast<uint2*>(p.attn + head * HD + lane * 4) = *reinterpret_cast<const uint2*>(ob);
+    *reinterpret_cast<uint2*>(xs + head * HD + l4 * 4) = *reinterpret_cast<const uint2*>(ob);
   }
-  if (threadIdx.x == 0) p.tickets[kvh] = 0u;
+  cbar_sync();
 }
 
 // ---------------------------------------------------------------------------------
@@ -516,16 +549,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   }
   __syncthreads();
 
-  if (warp == MK_CW) {
-    // ===== PRODUCER: never waits for activations; runs ahead across phases and layers =====
-    mk_producer(p, ring, lane);
+  volatile unsigned int* consumed = reinterpret_cast<volatile unsigned int*>(red + 48);
+  if (threadIdx.x == 0) *consumed = 0u;
+  __syncthreads();
+  if (warp >= MK_CW) {
+    // ===== PRODUCERS / PREFETCHER: never wait for activations; run ahead across phases and layers =====
+    if (warp < MK_CW + MK_PW) mk_producer(p, ring, lane, warp - MK_CW);
+    else mk_prefetcher(p, lane, consumed);
     return;
   }
 
   // ===== CONSUMERS =====
   const int cw = warp;
   bf16* xs = reinterpret_cast<bf16*>(scratch);
-  unsigned int bar_k = 0;
+  unsigned int bar_k = 0, ncons = 0;
   const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
   const int pos = p.st->pos;
   const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(p.st->token, 0), p.vocab - 1) * p.H : p.x_in;
@@ -536,7 +573,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
 
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
-    mk_consume(p, PH_QKV, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_QKV, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       const int task = vr >> 1, which = vr & 1;
       const int slot = task >> 6, d = task & 63;
       int kind = 0, hrow = slot;
@@ -570,9 +607,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_attention<G>(p, L, scratch, cw, lane);
     mk_grid_barrier(p, bar_base, bar_k);
 
-    // ---- P3: o_proj + residual
-    mk_stage_copy(xs, p.attn, p.n_heads * HD);
-    mk_consume(p, PH_O, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+    // ---- P3: merge attention splits -> o_proj + residual
+    mk_stage_attn_merge(xs, p);
+    mk_consume(p, PH_O, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       if (!owner) return;
       const float o = bf16r(v);
       const unsigned short xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
@@ -582,7 +619,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
-    mk_consume(p, PH_GU, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_GU, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       const float y = bf16r(v);
       const float u = __shfl_xor_sync(0xffffffffu, y, 16);
       if (!owner || (vr & 1)) return;
@@ -594,7 +631,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
-    mk_consume(p, PH_DOWN, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_DOWN, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       if (!owner) return;
       const float o = bf16r(v);
       const unsigned short hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
@@ -609,7 +646,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_stage_rmsnorm(xs, red, cur, p.norm_w, p.H, p.eps);
     float hm = -INFINITY, hl = 0.f;
     int hi = 0x7fffffff;
-    mk_consume(p, PH_HEAD, ring, xs, cw, lane, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_HEAD, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       if (!owner) return;
       const float lg = bf16r(v);
       p.logits_bf16[vr] = __float2bfloat16_rn(v);
@@ -671,7 +708,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (p.advance) p.st->pos = pos + 1;
-    *p.bar_epoch = bar_base + bar_k * gridDim.x;   // every CTA passed bar_k barriers; next launch starts here
+    if (!(p.flags & 1)) *p.bar_epoch = bar_base + bar_k * gridDim.x;   // every CTA passed bar_k barriers; next launch starts here
   }
 }
 
