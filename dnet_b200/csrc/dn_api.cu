@@ -39,6 +39,7 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
+static int g_mk_debug = 0;
 static int g_pf_depth = 10;   // megakernel producer: L2 prefetch look-ahead in 32 KB ring stages
 static int g_sms = 0;
 static int g_device = -1;
@@ -102,6 +103,8 @@ struct dn_model {
   std::vector<MkLayer> mk_host;
   MkLayer* mk_dev = nullptr;
   bf16 *xa = nullptr, *xb = nullptr;
+  unsigned long long* mk_dbg = nullptr;
+  size_t mk_dbg_words = 0;
   unsigned int* mk_sync = nullptr;   // [0] barrier count, [1] generation, [2] error, [3] head ticket
 };
 
@@ -202,6 +205,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!key) return fail(DN_EINVAL, "null option key");
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
+  if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
   if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
   if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
   return fail(DN_EINVAL, "unknown option '%s'", key);
@@ -280,7 +284,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   if (!m) return DN_OK;
   cudaFree(m->hbuf); cudaFree(m->qbuf); cudaFree(m->attn); cudaFree(m->act); cudaFree(m->logits_bf16);
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
-  cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
+  cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
   delete m;
   return DN_OK;
 }
@@ -616,11 +620,24 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
   p.flags = g_mk_flags;
+  p.dbg = nullptr;
+  if (g_mk_debug) {
+    const size_t words = (size_t)g_sms * (n > 0 ? n : 1) * 16;
+    if (m->mk_dbg_words < words) {
+      cudaFree(m->mk_dbg);
+      CK(cudaMalloc(&m->mk_dbg, words * 8));
+      m->mk_dbg_words = words;
+    }
+    p.dbg = m->mk_dbg;
+  }
   p.bar_gen = m->mk_sync + 4;
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
   const int attn_bytes = 2 * PAGE * HD * 2 + 8 * 32 * 4 + 64;
   if (scratch < attn_bytes) scratch = attn_bytes;
+  const int merge_bytes = c.n_heads * HD * 2 + c.n_heads * m->nsplit * 8 + 64;   // o_proj vector + (m,l) table
+  if (scratch < merge_bytes) scratch = merge_bytes;
+  if (c.hidden > 8192) return fail(DN_EINVAL, "hidden > 8192 unsupported by the step kernel's RMSNorm staging");
   scratch = (scratch + 1023) / 1024 * 1024;
   const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4;
   int stages = (227 * 1024 - scratch - tail) / MK_STAGE_BYTES;
@@ -643,6 +660,16 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   if (e != cudaSuccess) return fail(DN_ECUDA, "k_shard_step launch: %s", cudaGetErrorString(e));
   if (advance && !g_capturing) kv->host_pos += 1;
   return DN_OK;
+}
+
+// phase timestamps of the last dn_shard_step run with option mk_debug=1: [sm][layer][16] ns
+extern "C" int dn_step_debug(dn_model* m, unsigned long long* out_host, size_t max_words, dn_stream s) {
+  if (!m || !out_host) return fail(DN_EINVAL, "null argument");
+  if (!m->mk_dbg) return fail(DN_ENOENT, "no debug stamps recorded (set option mk_debug=1 first)");
+  const size_t n = m->mk_dbg_words < max_words ? m->mk_dbg_words : max_words;
+  CK(cudaMemcpyAsync(out_host, m->mk_dbg, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  CK(cudaStreamSynchronize((cudaStream_t)s));
+  return (int)(n / 16);
 }
 
 // 0 = clean; 2/3 = a bounded spin inside k_shard_step timed out (results of that step are invalid)

@@ -70,6 +70,7 @@ struct MkParams {
   int pf_depth;           // L2 prefetch look-ahead of the producer, in ring stages
   int flags;              // bit0: two-word (count + generation) grid barrier; bit1: nested-loop producer without L2 prefetch
   unsigned int* bar_gen;
+  unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
 };
 
@@ -114,16 +115,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     }
   }
 }
+// L2 eviction policies: weights are read exactly once per step, so demand loads are marked
+// evict-first (they must not push KV pages, activations or prefetched tiles out of L2) and
+// look-ahead prefetches evict-last (they must survive until the ring asks for them)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // TMA bulk copy global -> shared, completion counted on an mbarrier
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                    smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 // bulk L2 prefetch: pulls the bytes toward L2 without occupying a ring stage
-__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MK_CTHREADS) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
@@ -237,6 +251,7 @@ struct MkRing {
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLayer& L, int ph, MkRing& ring, int lane,
                                                  int which, unsigned int& idx) {
+  const uint64_t pol = l2_policy_evict_first();
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
@@ -252,7 +267,7 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
         __syncwarp();
         if (lane < nv)
           tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes,
-                       src + (size_t)sg * d.seg, rowbytes, &ring.full[ring.stage]);
+                       src + (size_t)sg * d.seg, rowbytes, &ring.full[ring.stage], pol);
       }
       ++idx;
       ring.advance();
@@ -279,6 +294,7 @@ __device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int
 // barrier / staging / attention) and the ring then refills at L2 speed.
 __device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLayer& L, int ph, int lane, unsigned int& n,
                                                   volatile unsigned int* consumed, unsigned int limit, bool& alive) {
+  const uint64_t pol = l2_policy_evict_last();
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
@@ -295,7 +311,7 @@ __device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLay
           if (gtimer() - t0 > MK_TIMEOUT_NS) { alive = false; return; }
         }
       }
-      if (src != nullptr) tma_prefetch_l2(src + (size_t)sg * d.seg, rowbytes);
+      if (src != nullptr) tma_prefetch_l2(src + (size_t)sg * d.seg, rowbytes, pol);
       ++n;
     }
   }
@@ -380,15 +396,25 @@ __device__ __forceinline__ void mk_stage_copy(bf16* xs, const bf16* src, int K) 
     reinterpret_cast<uint4*>(xs)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
   cbar_sync();
 }
-// RMSNorm staging (same arithmetic and summation structure as stage_rmsnorm<1>)
+// RMSNorm staging (same arithmetic and summation structure as stage_rmsnorm<1>); x and w are
+// fetched once and kept in registers across the block reduction (K <= 8192), so the phase
+// start costs one L2 round trip instead of two.
 __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const bf16* src, const bf16* w, int K, float eps) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int MAXIT = 4;
+  uint4 gv[MAXIT];
   float ss = 0.f;
-  for (int i = tid * 8; i < K; i += MK_CTHREADS * 8) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
-    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  for (int it = 0; it < MAXIT; ++it) {
+    const int i = tid * 8 + it * MK_CTHREADS * 8;
+    if (i < K) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
+      gv[it] = *reinterpret_cast<const uint4*>(w + i);
+      *reinterpret_cast<uint4*>(xs + i) = v;           // raw x parked in shared memory, normalised in place below
+      const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    }
   }
   ss = warp_sum(ss);
   cbar_sync();
@@ -398,17 +424,30 @@ __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const
 #pragma unroll
   for (int i = 0; i < MK_CW; ++i) tot += scratch[i];
   const float inv = 1.0f / sqrtf(tot / (float)K + eps);
-  for (int i = tid * 8; i < K; i += MK_CTHREADS * 8) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
-    const uint4 g = *reinterpret_cast<const uint4*>(w + i);
-    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
-    const float gw[8] = {bf_lo(g.x), bf_hi(g.x), bf_lo(g.y), bf_hi(g.y), bf_lo(g.z), bf_hi(g.z), bf_lo(g.w), bf_hi(g.w)};
-    __align__(16) bf16 o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fmul_rn(bf16r(__fmul_rn(f[j], inv)), gw[j]));
-    *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(o);
+  for (int it = 0; it < MAXIT; ++it) {
+    const int i = tid * 8 + it * MK_CTHREADS * 8;
+    if (i < K) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xs + i), g = gv[it];
+      const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+      const float gw[8] = {bf_lo(g.x), bf_hi(g.x), bf_lo(g.y), bf_hi(g.y), bf_lo(g.z), bf_hi(g.z), bf_lo(g.w), bf_hi(g.w)};
+      __align__(16) bf16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(__fmul_rn(bf16r(__fmul_rn(f[j], inv)), gw[j]));
+      *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(o);
+    }
   }
   cbar_sync();
+}
+
+// attention split geometry shared by the attention phase and the merge: splits are chunks of
+// tokens (multiples of 32), so a short context still spreads over many CTAs
+__device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, int& chunk, int& nact) {
+  int c = (kv_len + p.nsplit - 1) / p.nsplit;
+  c = (c + 31) / 32 * 32;           // 32-token granularity: short contexts -> ~kv_len/32 splits
+  if (c < 32) c = 32;
+  chunk = c;
+  nact = (kv_len + c - 1) / c;
 }
 
 // ---------------------------------------------------------------------------------
@@ -417,17 +456,15 @@ __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const
 template <int G>
 __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane) {
   const int kv_len = p.st->pos + 1;
-  const int npages = (kv_len + PAGE - 1) / PAGE;
-  const int nact = min(p.nsplit, npages);            // active splits (short contexts use few)
+  int chunk, nact;
+  mk_attn_geometry(p, kv_len, chunk, nact);
   const int task = blockIdx.x;
   if (task >= p.n_kv * nact) return;                  // CTA-uniform
   const int kvh = task / nact, sp = task % nact;
-  const int pps = (npages + nact - 1) / nact;
-  const int p0 = sp * pps, p1 = min(p0 + pps, npages);
+  const int t0 = sp * chunk, t1 = min(kv_len, t0 + chunk);
   bf16* Ks = reinterpret_cast<bf16*>(scratch);
   bf16* Vs = Ks + PAGE * HD;
   float* ps = reinterpret_cast<float*>(scratch + 2 * PAGE * HD * sizeof(bf16));   // [G][32]
-  int* s_last = reinterpret_cast<int*>(ps + G * 32);
   const int head = kvh * G + cw;
   const float scale = 0.08838834764831845f;
   float qv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -437,15 +474,17 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
     qv[2] = __fmul_rn(bf_lo(u.y), scale); qv[3] = __fmul_rn(bf_hi(u.y), scale);
   }
   float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int pg = p0; pg < p1; ++pg) {
-    const int phys = p.block_table[pg];
-    const uint4* ksrc = reinterpret_cast<const uint4*>(L.kv_pool + (((size_t)phys * 2 + 0) * p.n_kv + kvh) * (PAGE * HD));
-    const uint4* vsrc = reinterpret_cast<const uint4*>(L.kv_pool + (((size_t)phys * 2 + 1) * p.n_kv + kvh) * (PAGE * HD));
-    const int ntok = min(PAGE, kv_len - pg * PAGE);
-    const int n16 = ntok * HD / 8;
-    for (int i = threadIdx.x; i < n16; i += MK_CTHREADS) {
-      reinterpret_cast<uint4*>(Ks)[i] = __ldcg(ksrc + i);
-      reinterpret_cast<uint4*>(Vs)[i] = __ldcg(vsrc + i);
+  for (int tt = t0; tt < t1; tt += PAGE) {
+    const int ntok = min(PAGE, t1 - tt);
+    // tile of up to 64 tokens (may straddle a page boundary): one 256-byte K row + V row per token
+    for (int i = threadIdx.x; i < ntok * 16; i += MK_CTHREADS) {
+      const int tok = tt + (i >> 4), part = i & 15;
+      const int phys = p.block_table[tok / PAGE];
+      const size_t base = (((size_t)phys * 2) * p.n_kv + kvh) * (PAGE * HD) + (size_t)(tok % PAGE) * HD;
+      const uint4* ksrc = reinterpret_cast<const uint4*>(L.kv_pool + base);
+      const uint4* vsrc = reinterpret_cast<const uint4*>(L.kv_pool + base + (size_t)p.n_kv * (PAGE * HD));
+      reinterpret_cast<uint4*>(Ks)[i] = __ldcg(ksrc + part);
+      reinterpret_cast<uint4*>(Vs)[i] = __ldcg(vsrc + part);
     }
     cbar_sync();
     if (cw < G) {
@@ -496,28 +535,69 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
 // which removes the ticket + last-CTA merge + one more round trip from the critical path.
 __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p) {
   const int kv_len = p.st->pos + 1;
-  const int npages = (kv_len + PAGE - 1) / PAGE;
-  const int nact = min(p.nsplit, npages);
-  for (int gidx = threadIdx.x; gidx < p.n_heads * 32; gidx += MK_CTHREADS) {
-    const int head = gidx >> 5, l4 = gidx & 31;
-    const float* hp = p.part + ((size_t)head * p.nsplit) * PART_STRIDE;
-    float M = -INFINITY;
-    for (int s2 = 0; s2 < nact; ++s2) M = fmaxf(M, __ldcg(hp + (size_t)s2 * PART_STRIDE + 128));
-    float Lsum = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s2 = 0; s2 < nact; ++s2) {
-      const float ms = __ldcg(hp + (size_t)s2 * PART_STRIDE + 128);
-      if (ms == -INFINITY) continue;
-      const float w2 = exp2f((ms - M) * LOG2E);
-      Lsum = fmaf(__ldcg(hp + (size_t)s2 * PART_STRIDE + 129), w2, Lsum);
-      const float4 ov = __ldcg(reinterpret_cast<const float4*>(hp + (size_t)s2 * PART_STRIDE + l4 * 4));
-      acc[0] = fmaf(ov.x, w2, acc[0]); acc[1] = fmaf(ov.y, w2, acc[1]);
-      acc[2] = fmaf(ov.z, w2, acc[2]); acc[3] = fmaf(ov.w, w2, acc[3]);
-    }
-    const float invL = 1.0f / Lsum;
-    __align__(8) bf16 ob[4];
+  int chunk, nact;
+  mk_attn_geometry(p, kv_len, chunk, nact);
+  // (1) all (m, l) pairs in one parallel round trip -> shared memory (behind the activation vector)
+  float* ml = reinterpret_cast<float*>(xs + p.n_heads * HD);            // [n_heads][nact][2]
+  for (int i = threadIdx.x; i < p.n_heads * nact; i += MK_CTHREADS) {
+    const int head = i / nact, s2 = i % nact;
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(p.part + ((size_t)head * p.nsplit + s2) * PART_STRIDE + 128));
+    ml[2 * i] = v.x; ml[2 * i + 1] = v.y;
+  }
+  cbar_sync();
+  // (2) each thread merges 2 float4 groups per round and fetches 4 splits of both at once
+  //     (8 independent 16-byte loads in flight; more would spill in the GEMV hot loops)
+  const int ngrp = p.n_heads * 32;
+  for (int g0 = threadIdx.x; g0 < ngrp; g0 += MK_CTHREADS * 2) {
+    float acc[2][4], Lsum[2], M[2];
+    const float* hp[2];
+    const float* hml[2];
+    bool ok[2];
 #pragma unroll
-    for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(acc[dd] * invL);
-    *reinterpret_cast<uint2*>(xs + head * HD + l4 * 4) = *reinterpret_cast<const uint2*>(ob);
+    for (int q = 0; q < 2; ++q) {
+      const int gidx = g0 + q * MK_CTHREADS;
+      ok[q] = gidx < ngrp;
+      const int head = ok[q] ? (gidx >> 5) : 0, l4 = gidx & 31;
+      hp[q] = p.part + ((size_t)head * p.nsplit) * PART_STRIDE + l4 * 4;
+      hml[q] = ml + 2 * head * nact;
+      float mm = -INFINITY;
+      for (int s2 = 0; s2 < nact; ++s2) mm = fmaxf(mm, hml[q][2 * s2]);
+      M[q] = mm; Lsum[q] = 0.f;
+      acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    }
+#pragma unroll 1
+    for (int s0 = 0; s0 < nact; s0 += 4) {
+      float4 ov[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ok[q] && s0 + j < nact) ov[q][j] = __ldcg(reinterpret_cast<const float4*>(hp[q] + (size_t)(s0 + j) * PART_STRIDE));
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ok[q] && s0 + j < nact) {
+            const float ms = hml[q][2 * (s0 + j)];
+            if (ms != -INFINITY) {                     // fixed order over splits -> deterministic
+              const float w2 = exp2f((ms - M[q]) * LOG2E);
+              Lsum[q] = fmaf(hml[q][2 * (s0 + j) + 1], w2, Lsum[q]);
+              acc[q][0] = fmaf(ov[q][j].x, w2, acc[q][0]); acc[q][1] = fmaf(ov[q][j].y, w2, acc[q][1]);
+              acc[q][2] = fmaf(ov[q][j].z, w2, acc[q][2]); acc[q][3] = fmaf(ov[q][j].w, w2, acc[q][3]);
+            }
+          }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!ok[q]) continue;
+      const int gidx = g0 + q * MK_CTHREADS;
+      const float invL = 1.0f / Lsum[q];
+      __align__(8) bf16 ob[4];
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(acc[q][dd] * invL);
+      *reinterpret_cast<uint2*>(xs + (gidx >> 5) * HD + (gidx & 31) * 4) = *reinterpret_cast<const uint2*>(ob);
+    }
   }
   cbar_sync();
 }
@@ -567,12 +647,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   const int pos = p.st->pos;
   const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(p.st->token, 0), p.vocab - 1) * p.H : p.x_in;
 
+#define MK_STAMP(i) do { if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * 16 + (i)] = gtimer(); } while (0)
   for (int li = 0; li < p.n_layers; ++li) {
     const MkLayer L = p.layers[li];
     bf16* nxt = (li == p.n_layers - 1) ? p.x_out : ((li & 1) ? p.xb : p.xa);
+    MK_STAMP(0);
 
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
+    MK_STAMP(1);
     mk_consume(p, PH_QKV, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       const int task = vr >> 1, which = vr & 1;
       const int slot = task >> 6, d = task & 63;
@@ -601,24 +684,32 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
         L.kv_pool[off] = __float2bfloat16_rn(o);
       }
     });
+    MK_STAMP(2);
     mk_grid_barrier(p, bar_base, bar_k);
+    MK_STAMP(3);
 
-    // ---- P2: paged-KV attention (split over pages, last-CTA merge)
+    // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
     mk_attention<G>(p, L, scratch, cw, lane);
+    MK_STAMP(4);
     mk_grid_barrier(p, bar_base, bar_k);
+    MK_STAMP(5);
 
     // ---- P3: merge attention splits -> o_proj + residual
     mk_stage_attn_merge(xs, p);
+    MK_STAMP(6);
     mk_consume(p, PH_O, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       if (!owner) return;
       const float o = bf16r(v);
       const unsigned short xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
       p.hbuf[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(xb_)), o));
     });
+    MK_STAMP(7);
     mk_grid_barrier(p, bar_base, bar_k);
+    MK_STAMP(8);
 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
+    MK_STAMP(9);
     mk_consume(p, PH_GU, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       const float y = bf16r(v);
       const float u = __shfl_xor_sync(0xffffffffu, y, 16);
@@ -627,17 +718,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const float a = bf16r(__fmul_rn(y, s));
       p.act[vr >> 1] = __float2bfloat16_rn(__fmul_rn(a, u));
     });
+    MK_STAMP(10);
     mk_grid_barrier(p, bar_base, bar_k);
+    MK_STAMP(11);
 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
+    MK_STAMP(12);
     mk_consume(p, PH_DOWN, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
       if (!owner) return;
       const float o = bf16r(v);
       const unsigned short hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
       nxt[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(hb)), o));
     });
+    MK_STAMP(13);
     mk_grid_barrier(p, bar_base, bar_k);
+    MK_STAMP(14);
     cur = nxt;
   }
 

@@ -126,7 +126,9 @@ int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, void* x_ino
 int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
                   int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
                   float* logits_f32_out, int advance, dn_stream s);
-int dn_step_error(dn_model* m, dn_stream s);      /* 0, or the code of a timed-out in-kernel wait */
+int dn_step_error(dn_model* m, dn_stream s);
+/* measurement hook: per-phase globaltimer stamps [sm][layer][16] of the last step (option mk_debug=1) */
+int dn_step_debug(dn_model* m, unsigned long long* out_host, size_t max_words, dn_stream s);      /* 0, or the code of a timed-out in-kernel wait */
 /* measurement hooks for bench.py: per-kernel device times (CUDA events on stream s between
  * the five launches of one layer: qkv+rope+append, attention, o_proj, gate/up, down) */
 int dn_layer_forward_timed(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s,
