@@ -40,7 +40,8 @@ static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
 static int g_mk_debug = 0;
-static int g_pf_depth = 10;   // megakernel producer: L2 prefetch look-ahead in 32 KB ring stages
+static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
+                              // harmful beyond -- 148 SMs x depth x 32 KB must stay well inside one L2 partition)
 static int g_sms = 0;
 static int g_device = -1;
 static bool g_capturing = false;

@@ -298,12 +298,16 @@ __device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLay
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(d, r0, r1);
-  const int nseg = d.K / d.seg;
-  const uint32_t rowbytes = (uint32_t)d.seg * 2u;
+  // One prefetch op covers up to 8 KiB of a row (4 ring stages), not one 2 KiB segment: the TMA
+  // unit retires ~1 bulk op per 46 cycles whatever its size, and a prefetch per segment doubles
+  // the op count (measured: look-ahead >= 16 stages dropped the step to 4.9 ms).
+  const int piece_cols = 4 * d.seg;                       // columns per prefetch op
+  const int npieces = (d.K + piece_cols - 1) / piece_cols;
   for (int rb = r0; rb < r1 && alive; rb += MK_ROWS) {
     const int nv = min(MK_ROWS, r1 - rb);
     const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
-    for (int sg = 0; sg < nseg; ++sg) {
+    for (int pc = 0; pc < npieces; ++pc) {
+      const int cols = min(piece_cols, d.K - pc * piece_cols);
       if ((int)(n - *consumed) > (int)limit) {
         const unsigned long long t0 = gtimer();
         while ((int)(n - *consumed) > (int)limit) {
@@ -311,8 +315,8 @@ __device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLay
           if (gtimer() - t0 > MK_TIMEOUT_NS) { alive = false; return; }
         }
       }
-      if (src != nullptr) tma_prefetch_l2(src + (size_t)sg * d.seg, rowbytes, pol);
-      ++n;
+      if (src != nullptr) tma_prefetch_l2(src + (size_t)pc * piece_cols, (uint32_t)cols * 2u, pol);
+      n += (unsigned int)(cols / d.seg);                  // ring stages covered by this piece
     }
   }
 }
