@@ -399,6 +399,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "step_error": int(lib.dn_step_error(rt.model._h, rt.compute_stream_ptr)),
                    "sequences_in_flight": 1},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "check": {"nonce0_token_after_steps": W + K, "token": dev_last_token},
     }
     print(json.dumps(out), flush=True)
     rt.unload_model_core()
@@ -416,6 +417,7 @@ def main():
     ap.add_argument("--l2-prefetch-kb", type=int, default=64)
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--mk-flags", type=int, default=0)
+    ap.add_argument("--fused-hop", type=int, default=1, help="N>1: wait+step+hop in one kernel")
     ap.add_argument("--pf-depth", type=int, default=-1, help="megakernel L2 prefetch look-ahead (ring stages); -1 = library default")
     ap.add_argument("--in-flight", type=int, default=0, help="sequences in flight at N>1 (default N)")
     ap.add_argument("--no-e2e", action="store_true")

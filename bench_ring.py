@@ -135,6 +135,20 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         _cabi.check(rc)
         graphs.append((gp.value, xptr))
 
+    fused = use_mk and bool(args.fused_hop)
+
+    def run_step_fused(n: int, st: int) -> None:
+        """wait + step + hop in ONE kernel launch (dn_shard_step_hop)"""
+        ns = states[n]
+        if last:
+            dst, dflag, dseq = tx.data_ptr + n * tx.ep.slot_bytes, tx.flag_ptr + n * 64, st + 2
+        else:
+            dst, dflag, dseq = tx.data_ptr + n * tx.ep.slot_bytes, tx.flag_ptr + n * 64, st + 1
+        _cabi.check(lib.dn_shard_step_hop(model._h, arr, len(mine), graphs[n][1], ns.kv._h, 1 if first else 0,
+                                          1 if last else 0, tok_local.data_ptr() + n * 64 if last else None,
+                                          lp_local.data_ptr() + n * 64 if last else None, 1,
+                                          rx.flag(n), st + 1, rx.slot(n) if first else None, dst, dflag, dseq, s))
+
     def run_step(n: int) -> None:
         """one shard step of nonce n on the compute stream"""
         ns = states[n]
@@ -165,6 +179,9 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         for _ in range(nsteps):
             st = step_no[0]
             for n in nonces:
+                if fused and use_ipc:
+                    run_step_fused(n, st)
+                    continue
                 if use_ipc:
                     rx.wait(n, st + 1, s)
                 else:
@@ -222,6 +239,12 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     dist.barrier()
     tw1 = time.perf_counter()
     ms_local = e0.elapsed_time(e1)
+    # nonce 0's token after W+K decode steps: must equal the 1-shard run's (bench.py N=1 "check")
+    chk = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if last:
+        chk.copy_(tok_local[0:1])
+    dist.broadcast(chk, src=world - 1)
+    check_token = int(chk.item())
     launches = int(lib.dn_launch_count() - l0)
     t = torch.tensor([ms_local], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,10 +370,12 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                                    f"(BASELINE configs[1]), {NS} sequences in flight (one per shard), each bs=1",
                        "prompt_len": PROMPT_LEN, "kv": "fp16 paged (64-token pages)", "wire_dtype": "bf16",
                        "l2": "inputs larger than L2 (>=1.7 GB of weights per shard step vs 126 MB L2); no flush",
-                       "pdl": bool(args.pdl), "step_kernel": "k_shard_step" if use_mk else "per-op kernels in a CUDA graph", "sequences_in_flight": NS, "hop": transport,
+                       "pdl": bool(args.pdl), "step_kernel": "k_shard_step" if use_mk else "per-op kernels in a CUDA graph", "sequences_in_flight": NS, "hop": transport + (" fused into k_shard_step (dn_shard_step_hop)" if (fused and use_ipc) else " (dn_hop_wait / dn_hop_send kernels)"),
                        "split": [f"{x[0]}-{x[-1]}" for x in split]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": None,
             "hop_timeout": bool(int(timed_out.item())),
+            "check": {"nonce0_token_after_steps": W + K, "token": check_token,
+                      "note": "equals the N=1 line's check.token for the same --steps/--warmup (split is bit-exact)"},
         }
         print(json.dumps(out), flush=True)
     sampler.stop()

@@ -585,9 +585,42 @@ static cudaError_t launch_step(const MkParams& p, size_t smem, cudaStream_t s) {
   return cudaLaunchKernelEx(&cfg, k_shard_step<G>, p);
 }
 
+struct HopArgs {
+  const uint32_t* wait_flag = nullptr; uint32_t wait_seq = 0;
+  const int32_t* token_in = nullptr;
+  void* send_dst = nullptr; uint32_t* send_flag = nullptr; uint32_t send_seq = 0;
+};
+static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                           int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
+                           float* logits_f32_out, int advance, const HopArgs& hop, dn_stream s);
+
 extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
                              int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
                              float* logits_f32_out, int advance, dn_stream s) {
+  return shard_step_impl(m, abs_layers, n, x_inout, kv, embed_from_token, do_head, token_out, logprob_out,
+                         logits_f32_out, advance, HopArgs(), s);
+}
+
+// dn_shard_step with the ring hop fused into the kernel: it spins (bounded) on wait_flag >= wait_seq
+// before reading its input (x_inout, or token_in on the first shard) while the weight ring already
+// fills, and at the end stores its result (activation, or the sampled token on the last shard) into
+// the successor's slot send_dst and releases send_flag = send_seq at system scope.  Any of the three
+// groups may be NULL.  Replaces dn_hop_wait + dn_shard_step + dn_hop_send (two launches per hop).
+extern "C" int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                                 int embed_from_token, int do_head, int32_t* token_out, float* logprob_out, int advance,
+                                 const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
+                                 void* send_dst, uint32_t* send_flag, uint32_t send_seq, dn_stream s) {
+  HopArgs h;
+  h.wait_flag = wait_flag; h.wait_seq = wait_seq; h.token_in = token_in;
+  h.send_dst = send_dst; h.send_flag = send_flag; h.send_seq = send_seq;
+  if (send_dst && !send_flag) return fail(DN_EINVAL, "send_dst without send_flag");
+  return shard_step_impl(m, abs_layers, n, x_inout, kv, embed_from_token, do_head, token_out, logprob_out, nullptr,
+                         advance, h, s);
+}
+
+static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                           int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
+                           float* logits_f32_out, int advance, const HopArgs& hop, dn_stream s) {
   if (!m || !x_inout || !kv || n < 0 || (n > 0 && !abs_layers)) return fail(DN_EINVAL, "bad argument");
   if (kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
   if (n == 0 && !do_head) return fail(DN_EINVAL, "nothing to do");
@@ -620,6 +653,8 @@ extern "C" int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void
   p.token_out = token_out; p.logprob_out = logprob_out; p.do_head = do_head ? 1 : 0; p.advance = advance ? 1 : 0;
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
+  p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
+  p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;
   p.dbg = nullptr;
   if (g_mk_debug) {

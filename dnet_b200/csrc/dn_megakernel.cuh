@@ -70,6 +70,11 @@ struct MkParams {
   int pf_depth;           // L2 prefetch look-ahead of the producer, in ring stages
   int flags;              // bit0: two-word (count + generation) grid barrier; bit1: nested-loop producer without L2 prefetch
   unsigned int* bar_gen;
+  // fused ring hop (all optional): wait for the predecessor's flag before touching the input,
+  // publish the result into the successor's slot + flag at the end -- no separate hop kernels
+  const uint32_t* wait_flag; uint32_t wait_seq;
+  const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
+  void* send_dst; uint32_t* send_flag; uint32_t send_seq;
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
 };
@@ -648,8 +653,26 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   bf16* xs = reinterpret_cast<bf16*>(scratch);
   unsigned int bar_k = 0, ncons = 0;
   const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
+  if (p.wait_flag != nullptr) {
+    // the weights of this step are already streaming into the ring while we wait for the hop
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flag) : "memory");
+      if ((int32_t)(v - p.wait_seq) < 0) {
+        const unsigned long long t0 = gtimer();
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flag) : "memory");
+          if ((int32_t)(v - p.wait_seq) >= 0) break;
+          if (gtimer() - t0 > 5ull * MK_TIMEOUT_NS) { atomicExch(p.err, 4u); break; }
+        }
+      }
+      __threadfence();
+    }
+    cbar_sync();
+  }
   const int pos = p.st->pos;
-  const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(p.st->token, 0), p.vocab - 1) * p.H : p.x_in;
+  const int tok_in = p.token_in != nullptr ? __ldcg(p.token_in) : p.st->token;
+  const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(tok_in, 0), p.vocab - 1) * p.H : p.x_in;
 
 #define MK_STAMP(i) do { if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * 16 + (i)] = gtimer(); } while (0)
   for (int li = 0; li < p.n_layers; ++li) {
@@ -802,9 +825,23 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
         if (p.logprob_out != nullptr) *p.logprob_out = lp;
         p.st->token = idx;
         *p.head_ticket = 0u;
+        if (p.send_dst != nullptr) *reinterpret_cast<volatile int32_t*>(p.send_dst) = idx;   // token hop to shard 0
         __threadfence_system();
+        if (p.send_flag != nullptr)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.send_flag), "r"(p.send_seq) : "memory");
       }
     }
+  }
+  if (!p.do_head && p.send_dst != nullptr && blockIdx.x == 0) {
+    // activation hop: every CTA passed the barrier after the last down-proj, so x_out is complete;
+    // CTA 0 stores it into the successor's slot over NVLink and releases the sequence flag
+    const uint4* src4 = reinterpret_cast<const uint4*>(p.x_out);
+    uint4* dst4 = reinterpret_cast<uint4*>(p.send_dst);
+    for (int i = threadIdx.x; i < p.H / 8; i += MK_CTHREADS) dst4[i] = __ldcg(src4 + i);
+    __threadfence_system();
+    cbar_sync();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.send_flag), "r"(p.send_seq) : "memory");
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (p.advance) p.st->pos = pos + 1;

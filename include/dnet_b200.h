@@ -126,6 +126,14 @@ int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, void* x_ino
 int dn_shard_step(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
                   int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
                   float* logits_f32_out, int advance, dn_stream s);
+/* dn_shard_step with the ring hop fused into the kernel (compute + peer stores over NVLink in one
+ * launch): waits for wait_flag >= wait_seq before reading its input, publishes its result into the
+ * successor's slot + flag at the end.  Replaces RingAdapter._send_activation / ingress for the
+ * tensor bytes (shard/adapters/ring.py:161-206,265-299) without any separate hop kernel. */
+int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
+                      int embed_from_token, int do_head, int32_t* token_out, float* logprob_out, int advance,
+                      const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
+                      void* send_dst, uint32_t* send_flag, uint32_t send_seq, dn_stream s);
 int dn_step_error(dn_model* m, dn_stream s);
 /* measurement hook: per-phase globaltimer stamps [sm][layer][16] of the last step (option mk_debug=1) */
 int dn_step_debug(dn_model* m, unsigned long long* out_host, size_t max_words, dn_stream s);      /* 0, or the code of a timed-out in-kernel wait */

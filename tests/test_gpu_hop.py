@@ -75,3 +75,54 @@ def test_slot_prefetch_pinned_to_hbm_with_event(cuda_lib):
 
 def test_launch_counter_counts_graph_nodes(cuda_lib):
     assert cuda_lib.dn_launch_count() >= 0 and cuda_lib.dn_device_sm_count() >= 100
+
+
+def test_fused_hop_step_matches_unfused(cuda_lib):
+    """dn_shard_step_hop on one device (self-loop slots): waits on a pre-set flag, computes the
+    same step as dn_shard_step, and publishes activation + flag / token + flag."""
+    from tests.helpers import load_golden, make_runtime, oracle_weights, token_message
+    lib = cuda_lib
+    g = load_golden("tiny_llama")
+    cfgd = g["config"]
+    w = oracle_weights(cfgd, g["wseed"])
+    H = cfgd["hidden_size"]
+    a = make_runtime(cfgd, w, [0, 1], shard_id="a")
+    b = make_runtime(cfgd, w, [2, 3], shard_id="b")
+    try:
+        # prefill both shards through the policy (unfused), take the first token
+        a.policy.process(token_message(a, "n", g["prompt"].tolist()))
+        mid = a.activation_send_queue.get_nowait()
+        b.policy.process(mid)
+        first = b.activation_send_queue.get_nowait()
+        assert first.is_final and first.token_id == int(g["tokens"][0])
+        nsa, nsb = a._kv_by_nonce["n"], b._kv_by_nonce["n"]
+        slot, flags = C.c_void_p(), C.c_void_p()
+        _cabi.check(lib.dn_hop_alloc(H * 2 + 64, C.byref(slot)))     # activation slot for b (+ token line)
+        _cabi.check(lib.dn_hop_alloc(256, C.byref(flags)))
+        tokslot = torch.tensor([first.token_id, 0, 0, 0], dtype=torch.int32, device="cuda")
+        tok_out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        lp_out = torch.zeros(4, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        sa, sb = a.compute_stream_ptr, b.compute_stream_ptr
+        la = (C.c_int32 * 2)(0, 1)
+        lb = (C.c_int32 * 2)(2, 3)
+        toks = []
+        for step in range(1, 6):
+            # shard a: token_in = tokslot, no wait; sends its activation into `slot`, flag[0] = step
+            _cabi.check(lib.dn_shard_step_hop(a.model._h, la, 2, nsa.x1.data_ptr(), nsa.kv._h, 1, 0, None, None, 1,
+                                              None, 0, tokslot.data_ptr(), slot.value, flags.value, step, sa))
+            # shard b: waits for flag[0] >= step, computes in place in the slot, samples, sends the token back
+            _cabi.check(lib.dn_shard_step_hop(b.model._h, lb, 2, slot.value, nsb.kv._h, 0, 1, tok_out.data_ptr(),
+                                              lp_out.data_ptr(), 1, flags.value, step, None, tokslot.data_ptr(),
+                                              flags.value + 64, step, sb))
+            b.compute_stream.synchronize()
+            a.compute_stream.synchronize()
+            toks.append(int(tok_out[0].item()))
+            assert int(tokslot[0].item()) == toks[-1]
+        assert toks == g["tokens"][1:6].tolist()
+        assert lib.dn_step_error(a.model._h, sa) == 0 and lib.dn_step_error(b.model._h, sb) == 0
+        _cabi.check(lib.dn_hop_free(slot.value))
+        _cabi.check(lib.dn_hop_free(flags.value))
+    finally:
+        a.unload_model_core()
+        b.unload_model_core()
