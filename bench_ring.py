@@ -34,6 +34,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     from tests.helpers import token_message
 
     PROMPT_LEN = B.PROMPT_LEN
+    os.environ["NCCL_DEBUG"] = os.environ.get("DNET_NCCL_DEBUG", "WARN")   # stdout must stay ONE JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     gloo = dist.new_group(backend="gloo")
     lib = _cabi.load()
