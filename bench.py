@@ -216,7 +216,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------
@@ -235,6 +235,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     _cabi.init(local_rank)
     lib = _cabi.load()
     if world > 1:
+        import bench as _b                     # bench_ring imports `bench`; this file runs as __main__
+        _b._REAL_STDOUT, _b.PROMPT_LEN = _REAL_STDOUT, PROMPT_LEN
         from bench_ring import run_ring
         return run_ring(args, rank, local_rank, world)
 
@@ -416,11 +418,31 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "check": {"nonce0_token_after_steps": W + K, "token": dev_last_token},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     rt.unload_model_core()
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Everything any library prints to fd 1 (e.g. NCCL's version banner) goes to stderr; the one
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=256)

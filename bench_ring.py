@@ -378,7 +378,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
             "check": {"nonce0_token_after_steps": W + K, "token": check_token,
                       "note": "equals the N=1 line's check.token for the same --steps/--warmup (split is bit-exact)"},
         }
-        print(json.dumps(out), flush=True)
+        B.emit(out)
     sampler.stop()
     dist.barrier()
     rt.unload_model_core()
