@@ -74,6 +74,7 @@ _PROTOS = {
     "dn_layer_is_bound": (_i, [_vp, _i]),
     "dn_bind_api": (_i, [_vp, _vp, _vp, _vp]),
     "dn_model_max_chunk": (_i, [_vp]),
+    "dn_model_max_prefill_chunk": (_i, [_vp]),
     "dn_kv_create": (_i, [_vp, _i, C.POINTER(_vp)]),
     "dn_kv_free": (_i, [_vp]),
     "dn_kv_reset": (_i, [_vp, _vp]),

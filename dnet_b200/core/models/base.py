@@ -74,9 +74,14 @@ def _stream_ptr(stream) -> int:
     return int(stream.cuda_stream)
 
 
-def _decompose(T: int, tmax: int) -> List[int]:
-    """Split T into chunk sizes the kernels are instantiated for (4, 2, 1)."""
+def _decompose(T: int, tmax: int, big: int = 0) -> List[int]:
+    """Split T into chunk sizes the kernels are instantiated for: chunks of 16..``big`` tokens go
+    to the tensor-core prefill GEMMs, the remainder to the (4, 2, 1)-token GEMV kernels."""
     out: List[int] = []
+    while big >= 16 and T >= 16:
+        c = min(T, big)
+        out.append(c)
+        T -= c
     c = 4
     while c > tmax:
         c >>= 1
@@ -127,6 +132,7 @@ class BaseRingModel(ABC):
         self.hidden_size = cfg["hidden_size"]
         self.vocab_size = cfg["vocab_size"]
         self.max_chunk = int(self._lib.dn_model_max_chunk(self._h))
+        self.max_prefill_chunk = int(self._lib.dn_model_max_prefill_chunk(self._h))
 
     # -- abstract operator API -----------------------------------------------------------
     @abstractmethod
@@ -243,7 +249,7 @@ class BaseRingModel(ABC):
         arr = (C.c_int32 * len(layers))(*layers)
         base = cache.offset
         t0 = 0
-        chunks = _decompose(T, self.max_chunk)
+        chunks = _decompose(T, self.max_chunk, self.max_prefill_chunk)
         for c in chunks:
             if len(chunks) > 1:
                 cache.seek(base + t0, s)

@@ -4,6 +4,7 @@
 // layer-swap copies.  All arithmetic is in dn_kernels.cuh.
 #include "dn_kernels.cuh"
 #include "dn_megakernel.cuh"
+#include "dn_gemm_tc.cuh"
 #include "../../include/dnet_b200.h"
 
 #include <atomic>
@@ -79,7 +80,36 @@ static cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
 struct LayerW {
   const bf16* w[DN_W_COUNT];
   bool bound = false;
+  CUtensorMap tm[7];          // TMA descriptors of q,k,v,o,gate,up,down ([rows, K] bf16, box 128 x 64, SWIZZLE_128B)
+  bool tm_ok = false;
 };
+
+constexpr int TPF_MAX = 128;   // tokens per tensor-core prefill chunk
+static int g_tc_prefill = 1;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int make_tmap(CUtensorMap* out, const void* base, int rows, int cols, int box_rows) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return fail(DN_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    g_encode = (PFN_encodeTiled)fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DN_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+  return DN_OK;
+}
 
 struct dn_model {
   dn_model_cfg cfg;
@@ -104,6 +134,10 @@ struct dn_model {
   std::vector<MkLayer> mk_host;
   MkLayer* mk_dev = nullptr;
   bf16 *xa = nullptr, *xb = nullptr;
+  // tensor-core prefill scratch ([TPF_MAX][...]) and the TMA descriptors of the activation buffers
+  bf16 *pf_xn = nullptr, *pf_qkv = nullptr, *pf_q = nullptr, *pf_attn = nullptr, *pf_h = nullptr, *pf_act = nullptr;
+  CUtensorMap tm_xn64, tm_xn128, tm_attn64, tm_attn128, tm_act64, tm_act128;
+  bool pf_ok = false;
   unsigned long long* mk_dbg = nullptr;
   size_t mk_dbg_words = 0;
   unsigned int* mk_sync = nullptr;   // [0] barrier count, [1] generation, [2] error, [3] head ticket
@@ -206,6 +240,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!key) return fail(DN_EINVAL, "null option key");
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
+  if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
   if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
   if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
@@ -277,6 +312,22 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   CK(cudaMalloc(&m->xb, (size_t)H * 2));
   CK(cudaMalloc(&m->mk_sync, 64));
   CK(cudaMemset(m->mk_sync, 0, 64));
+  {
+    const int qkvd = (cfg->n_heads + 2 * cfg->n_kv_heads) * HD;
+    CK(cudaMalloc(&m->pf_xn, (size_t)TPF_MAX * H * 2));
+    CK(cudaMalloc(&m->pf_qkv, (size_t)TPF_MAX * qkvd * 2));
+    CK(cudaMalloc(&m->pf_q, (size_t)TPF_MAX * qd * 2));
+    CK(cudaMalloc(&m->pf_attn, (size_t)TPF_MAX * qd * 2));
+    CK(cudaMalloc(&m->pf_h, (size_t)TPF_MAX * H * 2));
+    CK(cudaMalloc(&m->pf_act, (size_t)TPF_MAX * cfg->ffn * 2));
+    CK(cudaMemset(m->pf_xn, 0, (size_t)TPF_MAX * H * 2));
+    CK(cudaMemset(m->pf_attn, 0, (size_t)TPF_MAX * qd * 2));
+    CK(cudaMemset(m->pf_act, 0, (size_t)TPF_MAX * cfg->ffn * 2));
+    m->pf_ok = (H % 128 == 0) && (qd % 128 == 0) && (cfg->ffn % 128 == 0) && ((cfg->n_kv_heads * HD) % 128 == 0) &&
+               make_tmap(&m->tm_xn64, m->pf_xn, TPF_MAX, H, 64) == DN_OK && make_tmap(&m->tm_xn128, m->pf_xn, TPF_MAX, H, 128) == DN_OK &&
+               make_tmap(&m->tm_attn64, m->pf_attn, TPF_MAX, qd, 64) == DN_OK && make_tmap(&m->tm_attn128, m->pf_attn, TPF_MAX, qd, 128) == DN_OK &&
+               make_tmap(&m->tm_act64, m->pf_act, TPF_MAX, cfg->ffn, 64) == DN_OK && make_tmap(&m->tm_act128, m->pf_act, TPF_MAX, cfg->ffn, 128) == DN_OK;
+  }
   *out = m;
   return DN_OK;
 }
@@ -285,12 +336,15 @@ extern "C" int dn_model_destroy(dn_model* m) {
   if (!m) return DN_OK;
   cudaFree(m->hbuf); cudaFree(m->qbuf); cudaFree(m->attn); cudaFree(m->act); cudaFree(m->logits_bf16);
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
+  cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
   cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
   delete m;
   return DN_OK;
 }
 
 extern "C" int dn_model_max_chunk(dn_model* m) { return m ? m->tmax : 0; }
+// largest chunk for the tensor-core prefill path (0 = unavailable); chunks must be >= 16 tokens
+extern "C" int dn_model_max_prefill_chunk(dn_model* m) { return (m && m->pf_ok && g_tc_prefill) ? TPF_MAX : 0; }
 
 extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_ptrs) {
   if (!m || !dev_ptrs) return fail(DN_EINVAL, "null argument");
@@ -303,6 +357,14 @@ extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_
     if (((uintptr_t)L.w[i]) & 15) return fail(DN_EINVAL, "layer %d: tensor %d is not 16-byte aligned", abs_layer, i);
   }
   L.bound = true;
+  {
+    const dn_model_cfg& c = m->cfg;
+    const int H = c.hidden, qd = c.n_heads * HD, kd = c.n_kv_heads * HD;
+    const int rows[7] = {qd, kd, kd, H, c.ffn, c.ffn, H};
+    const int cols[7] = {H, H, H, qd, H, H, c.ffn};
+    L.tm_ok = m->pf_ok;
+    for (int i = 0; i < 7 && L.tm_ok; ++i) L.tm_ok = make_tmap(&L.tm[i], L.w[i], rows[i], cols[i], TC_BM) == DN_OK;
+  }
   MkLayer& ML = m->mk_host[it->second];
   for (int i = 0; i < DN_W_COUNT; ++i) ML.w[i] = L.w[i];
   CK(cudaMemcpy(m->mk_dev + it->second, &ML, sizeof(MkLayer), cudaMemcpyHostToDevice));
@@ -458,10 +520,82 @@ static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, 
 static int head_common(dn_model* m, const void* x, int T, dn_kv* kv, int32_t* token_out, float* logprob_out,
                        float* logits_f32, cudaStream_t s);
 
+// ---- tensor-core prefill path (16 <= T <= TPF_MAX): tcgen05 GEMMs fed by TMA (dn_gemm_tc.cuh)
+template <int BN, int EPI, int STAGES>
+static cudaError_t launch_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap& x, const TcParams& p, cudaStream_t s) {
+  constexpr int NA = (EPI == EPI_SWIGLU) ? 2 : 1;
+  constexpr size_t smem = (size_t)STAGES * (NA * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int tiles = ((p.N + TC_BM - 1) / TC_BM) * ((p.T + BN - 1) / BN);
+  int grid = tiles < g_sms ? tiles : g_sms;
+  if (g_capturing) g_capture_launches++; else g_launches++;
+  k_gemm_tc<BN, EPI, STAGES><<<grid, TC_THREADS, smem, s>>>(w, w2, x, p);
+  return cudaGetLastError();
+}
+template <int EPI>
+static cudaError_t gemm_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap& x64, const CUtensorMap& x128,
+                           const TcParams& p, cudaStream_t s) {
+  if (p.T <= 64) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x64, p, s);
+  return launch_tc<128, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x128, p, s);
+}
+
+static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, cudaStream_t s) {
+  auto it = m->abs2local.find(abs_layer);
+  if (it == m->abs2local.end()) return fail(DN_ENOENT, "Layer %d not hosted on this model instance", abs_layer);
+  const int li = it->second;
+  LayerW& L = m->layers[li];
+  if (!L.bound) return fail(DN_ENOENT, "layer %d has no weights bound", abs_layer);
+  const dn_model_cfg& c = m->cfg;
+  const int H = c.hidden, qd = c.n_heads * HD, kd = c.n_kv_heads * HD, qkvd = qd + 2 * kd;
+  bf16* pool = m->kv_pool + (size_t)li * m->layer_elems;
+  unsigned int* err = m->mk_sync + 2;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.err = err;
+
+  k_rmsnorm_rows<<<T, 256, 0, s>>>(x, L.w[DN_W_LN1], m->pf_xn, H, c.rms_eps);
+  g_launches++;
+  p.K = H; p.Y = m->pf_qkv; p.ldy = qkvd;
+  p.N = qd; p.col0 = 0; p.bias = L.w[DN_W_QB];
+  CK(gemm_tc<EPI_STORE>(L.tm[0], L.tm[0], m->tm_xn64, m->tm_xn128, p, s));
+  p.N = kd; p.col0 = qd; p.bias = L.w[DN_W_KB];
+  CK(gemm_tc<EPI_STORE>(L.tm[1], L.tm[1], m->tm_xn64, m->tm_xn128, p, s));
+  p.col0 = qd + kd; p.bias = L.w[DN_W_VB];
+  CK(gemm_tc<EPI_STORE>(L.tm[2], L.tm[2], m->tm_xn64, m->tm_xn128, p, s));
+  p.bias = nullptr;
+  k_rope_append<<<dim3(c.n_heads + 2 * c.n_kv_heads, T), 128, 0, s>>>(m->pf_qkv, m->pf_q, pool, kv->block_table, kv->st, m->inv_freq,
+                                                                        c.n_heads, c.n_kv_heads);
+  g_launches++;
+  {
+    dim3 grid(c.n_kv_heads, (T + 3) / 4);
+#define PFA(Gv) case Gv: k_attn_prefill<Gv, 4><<<grid, Gv * 32, 0, s>>>(m->pf_q, pool, kv->block_table, kv->st, m->pf_attn, c.n_heads, c.n_kv_heads, T); break;
+    switch (m->G) { PFA(1) PFA(2) PFA(4) PFA(5) PFA(7) PFA(8) default: return fail(DN_EINVAL, "GQA group unsupported"); }
+#undef PFA
+    g_launches++;
+  }
+  p.K = qd; p.N = H; p.Y = m->pf_h; p.ldy = H; p.col0 = 0; p.resid = x; p.ldr = H;
+  CK(gemm_tc<EPI_RESID>(L.tm[3], L.tm[3], m->tm_attn64, m->tm_attn128, p, s));
+  k_rmsnorm_rows<<<T, 256, 0, s>>>(m->pf_h, L.w[DN_W_LN2], m->pf_xn, H, c.rms_eps);
+  g_launches++;
+  p.K = H; p.N = c.ffn; p.Y = m->pf_act; p.ldy = c.ffn; p.resid = nullptr;
+  CK(gemm_tc<EPI_SWIGLU>(L.tm[4], L.tm[5], m->tm_xn64, m->tm_xn128, p, s));
+  p.K = c.ffn; p.N = H; p.Y = x; p.ldy = H; p.resid = m->pf_h; p.ldr = H;
+  CK(gemm_tc<EPI_RESID>(L.tm[6], L.tm[6], m->tm_act64, m->tm_act128, p, s));
+  CK(cudaGetLastError());
+  return DN_OK;
+}
+
 static int check_fwd(dn_model* m, void* x, int T, dn_kv* kv) {
   if (!m || !x || !kv) return fail(DN_EINVAL, "null argument");
   if (kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
-  if (!(T == 1 || T == 2 || T == 4) || T > m->tmax) return fail(DN_EINVAL, "T=%d unsupported (1,2,4 up to %d)", T, m->tmax);
+  const bool tc_ok = g_tc_prefill && m->pf_ok && T >= 16 && T <= TPF_MAX;
+  if (!tc_ok && (!(T == 1 || T == 2 || T == 4) || T > m->tmax))
+    return fail(DN_EINVAL, "T=%d unsupported (1,2,4 up to %d, or 16..%d on the tensor-core prefill path)", T, m->tmax, TPF_MAX);
   if (!g_capturing && kv->host_pos + T > kv->max_tokens)
     return fail(DN_ENOSPC, "KV capacity exceeded: offset %d + %d > %d", kv->host_pos, T, kv->max_tokens);
   if (((uintptr_t)x) & 15) return fail(DN_EINVAL, "activation must be 16-byte aligned");
@@ -471,6 +605,7 @@ static int check_fwd(dn_model* m, void* x, int T, dn_kv* kv) {
 extern "C" int dn_layer_forward(dn_model* m, int abs_layer, void* x_inout, int T, dn_kv* kv, dn_stream s) {
   int rc = check_fwd(m, x_inout, T, kv);
   if (rc) return rc;
+  if (T >= 16) return layer_forward_tc(m, abs_layer, (bf16*)x_inout, T, kv, (cudaStream_t)s);
   return layer_forward(m, abs_layer, (bf16*)x_inout, T, kv, (cudaStream_t)s);
 }
 
@@ -524,7 +659,8 @@ extern "C" int dn_window_forward(dn_model* m, const int32_t* abs_layers, int n, 
   if (rc) return rc;
   if (n > 0 && !abs_layers) return fail(DN_EINVAL, "null layer list");
   for (int i = 0; i < n; ++i) {
-    rc = layer_forward(m, abs_layers[i], (bf16*)x_inout, T, kv, (cudaStream_t)s);
+    rc = T >= 16 ? layer_forward_tc(m, abs_layers[i], (bf16*)x_inout, T, kv, (cudaStream_t)s)
+                 : layer_forward(m, abs_layers[i], (bf16*)x_inout, T, kv, (cudaStream_t)s);
     if (rc) return rc;
   }
   return DN_OK;

@@ -1,0 +1,384 @@
+// dn_gemm_tc.cuh -- prefill GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged
+// by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B), warp-specialised: warp 0 = TMA producer, warp 1 =
+// single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld).
+//
+//   Y[T, N] = X[T, K] . W[N, K]^T        bf16 operands, fp32 accumulate in TMEM
+//
+// "swap-AB" orientation: the WEIGHT tile is the MMA's A operand (M = 128 output features per CTA
+// tile, one TMEM lane each) and the TOKEN tile is B (N = BN tokens = TMEM columns), because prefill
+// chunks have few tokens and many output features; both operands are K-major in shared memory,
+// exactly what TMA produces from the row-major [rows, K] tensors.  Each CTA walks n-tiles
+// persistently; per k-step (64 columns = one 128-byte swizzle span) four UMMA_K=16 instructions.
+//
+// Epilogues (fused, same rounding points as the decode kernels / oracle):
+//   EPI_STORE  : y = T(acc + bias)                        -> Y[t][col0 + n]
+//   EPI_RESID  : y = T(resid[t][n] + T(acc))              -> Y[t][n]
+//   EPI_SWIGLU : two weight tiles (gate, up) share the token tile; g = T(acc_g), u = T(acc_u),
+//                s = T(sigmoid g), a = T(g s), m = T(a u)  -> Y[t][n]
+#pragma once
+#include <cuda.h>
+#include "dn_megakernel.cuh"
+
+namespace dn {
+
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_SWIGLU = 2 };
+
+constexpr int TC_BM = 128;        // weight rows per tile (MMA M)
+constexpr int TC_BK = 64;         // k-step: 64 bf16 = 128 bytes = one swizzle span
+constexpr int TC_THREADS = 256;
+
+struct TcParams {
+  int T, N, K;                    // tokens, output features, reduction
+  int ldy, col0;                  // output leading dimension (elements) and column offset
+  bf16* Y;
+  const bf16* resid;              // [T][ldr]
+  int ldr;
+  const bf16* bias;               // [N] or null
+  unsigned int* err;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T   (kind::f16: bf16 x bf16 -> fp32)
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//  [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//  [32,46) stride byte offset >> 4 = 1024 B between 8-row groups | [46,48) version = 1 (sm_100) |
+//  [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t tc_smem_desc(const void* smem_ptr) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1)
+// at [7,10)/[10,13), a/b K-major (0) at 15/16, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t tc_instr_desc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 32 lanes x 16 consecutive fp32 columns of this warp's TMEM quarter
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, int EPI, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapW2,
+          const __grid_constant__ CUtensorMap mapX, const TcParams p) {
+  constexpr int NA = (EPI == EPI_SWIGLU) ? 2 : 1;
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = NA * A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (NA * BN <= 32) ? 32 : (NA * BN <= 64) ? 64 : (NA * BN <= 128) ? 128 : (NA * BN <= 256) ? 256 : 512;
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + TC_BM - 1) / TC_BM;
+  const int t_tiles = (p.T + BN - 1) / BN;
+  const int total_tiles = n_tiles * t_tiles;
+  const int k_steps = p.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);     // one arrival per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles, tt = tile / n_tiles;
+        for (int ks = 0; ks < k_steps; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1u, p.err);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          unsigned char* sa = smem + (size_t)stage * STAGE_BYTES;
+          tma_load_2d(sa, &mapW, ks * TC_BK, nt * TC_BM, &full[stage]);
+          if (NA == 2) tma_load_2d(sa + A_BYTES, &mapW2, ks * TC_BK, nt * TC_BM, &full[stage]);
+          tma_load_2d(sa + NA * A_BYTES, &mapX, ks * TC_BK, tt * BN, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc_instr_desc(TC_BM, BN);
+      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty, acc_phase ^ 1u, p.err);      // epilogue drained the accumulator
+        tc_fence_after();
+        for (int ks = 0; ks < k_steps; ++ks) {
+          mbar_wait(&full[stage], phase, p.err);
+          tc_fence_after();
+          unsigned char* sa = smem + (size_t)stage * STAGE_BYTES;
+          const uint64_t bdesc = tc_smem_desc(sa + NA * A_BYTES);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const uint64_t adesc = tc_smem_desc(sa + a * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle span
+              tc_mma(tmem_base + a * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);                   // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tmem_full);                         // accumulator complete -> epilogue
+        acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int ew = warp - 4;                          // TMEM lanes [32 ew, 32 ew + 32)
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles, tt = tile / n_tiles;
+      const int n = nt * TC_BM + ew * 32 + lane;      // output feature owned by this thread
+      mbar_wait(tmem_full, acc_phase, p.err);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+      float bias = 0.f;
+      if (EPI == EPI_STORE && p.bias != nullptr && n < p.N) bias = __bfloat162float(p.bias[n]);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        float v[16], v2[16];
+        tc_ld16(trow + c, v);
+        if (EPI == EPI_SWIGLU) tc_ld16(trow + BN + c, v2);
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int t = tt * BN + c + j;
+            if (t < p.T) {
+              float y;
+              if (EPI == EPI_STORE) {
+                y = v[j] + bias;
+              } else if (EPI == EPI_RESID) {
+                y = __fadd_rn(__bfloat162float(p.resid[(size_t)t * p.ldr + n]), bf16r(v[j]));
+              } else {
+                const float g = bf16r(v[j]), u = bf16r(v2[j]);
+                const float s = bf16r(1.0f / (1.0f + expf(-g)));
+                y = __fmul_rn(bf16r(__fmul_rn(g, s)), u);
+              }
+              p.Y[(size_t)t * p.ldy + p.col0 + n] = __float2bfloat16_rn(y);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// prefill helpers around the GEMMs
+// ---------------------------------------------------------------------------------
+// RMSNorm of T rows (same arithmetic as stage_rmsnorm): one CTA per token
+__global__ void __launch_bounds__(256) k_rmsnorm_rows(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ out,
+                                                      int K, float eps) {
+  __shared__ float scratch[8];
+  const bf16* xr = x + (size_t)blockIdx.x * K;
+  bf16* o = out + (size_t)blockIdx.x * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < K; i += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) scratch[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += scratch[i];
+  const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+  for (int i = threadIdx.x * 8; i < K; i += 256 * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 g = *reinterpret_cast<const uint4*>(w + i);
+    const float f[8] = {bf_lo(v.x), bf_hi(v.x), bf_lo(v.y), bf_hi(v.y), bf_lo(v.z), bf_hi(v.z), bf_lo(v.w), bf_hi(v.w)};
+    const float gw[8] = {bf_lo(g.x), bf_hi(g.x), bf_lo(g.y), bf_hi(g.y), bf_lo(g.z), bf_hi(g.z), bf_lo(g.w), bf_hi(g.w)};
+    __align__(16) bf16 ob[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ob[j] = __float2bfloat16_rn(__fmul_rn(bf16r(__fmul_rn(f[j], inv)), gw[j]));
+    *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(ob);
+  }
+}
+
+// RoPE on q (in place in the qkv buffer -> q_out) and k, and KV append, for T tokens.
+// qkv: [T][(n_heads + 2 n_kv) * 128] bf16 (Linear outputs already rounded to bf16)
+__global__ void __launch_bounds__(128) k_rope_append(const bf16* __restrict__ qkv, bf16* __restrict__ q_out, bf16* __restrict__ kv_pool,
+                                                     const int32_t* __restrict__ block_table, const StepState* __restrict__ st,
+                                                     const float* __restrict__ inv_freq, int n_heads, int n_kv) {
+  const int t = blockIdx.y, slot = blockIdx.x;            // slot: q heads, then k heads, then v heads
+  const int pos = st->pos + t;
+  const int ld = (n_heads + 2 * n_kv) * HD;
+  const bf16* src = qkv + (size_t)t * ld + (size_t)slot * HD;
+  const int d = threadIdx.x;                              // 0..127
+  const float y = __bfloat162float(src[d]);
+  int kind = 0, hrow = slot;
+  if (slot >= n_heads + n_kv) { kind = 2; hrow = slot - n_heads - n_kv; }
+  else if (slot >= n_heads) { kind = 1; hrow = slot - n_heads; }
+  float o = y;
+  if (kind != 2) {
+    const int dd = d & 63;
+    const float yp = __bfloat162float(src[d ^ 64]);
+    const float theta = __fmul_rn((float)pos, inv_freq[dd]);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    o = (d < 64) ? __fsub_rn(__fmul_rn(y, cs), __fmul_rn(yp, sn)) : __fadd_rn(__fmul_rn(yp, sn), __fmul_rn(y, cs));
+    o = bf16r(o);
+  }
+  if (kind == 0) {
+    q_out[(size_t)t * n_heads * HD + hrow * HD + d] = __float2bfloat16_rn(o);
+  } else {
+    const int page = block_table[pos / PAGE];
+    const size_t off = (((size_t)page * 2 + (kind - 1)) * n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + d;
+    kv_pool[off] = __float2bfloat16_rn(o);
+  }
+}
+
+// causal prefill attention over the paged KV: CTA = (kv head, group of QT query tokens); warp w
+// serves q head kvh*G + w for each of the QT tokens; K/V tiles are staged once per CTA.
+template <int G, int QT>
+__global__ void __launch_bounds__(G * 32) k_attn_prefill(const bf16* __restrict__ q, const bf16* __restrict__ kv_pool,
+                                                        const int32_t* __restrict__ block_table, const StepState* __restrict__ st,
+                                                        bf16* __restrict__ out, int n_heads, int n_kv, int T) {
+  __shared__ __align__(16) bf16 Ks[PAGE * HD];
+  __shared__ __align__(16) bf16 Vs[PAGE * HD];
+  __shared__ float ps[G][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kvh = blockIdx.x, t0 = blockIdx.y * QT;
+  const int head = kvh * G + warp;
+  const int pos0 = st->pos;
+  const int nq = min(QT, T - t0);
+  const int kv_max = pos0 + t0 + nq;                     // keys visible to the last query of this CTA
+  const float scale = 0.08838834764831845f;
+  float qv[QT][4], m[QT], l[QT], o[QT][4];
+#pragma unroll
+  for (int i = 0; i < QT; ++i) {
+    m[i] = -INFINITY; l[i] = 0.f;
+    o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    qv[i][0] = qv[i][1] = qv[i][2] = qv[i][3] = 0.f;
+    if (i < nq) {
+      const uint2 u = *reinterpret_cast<const uint2*>(q + (size_t)(t0 + i) * n_heads * HD + head * HD + lane * 4);
+      qv[i][0] = __fmul_rn(bf_lo(u.x), scale); qv[i][1] = __fmul_rn(bf_hi(u.x), scale);
+      qv[i][2] = __fmul_rn(bf_lo(u.y), scale); qv[i][3] = __fmul_rn(bf_hi(u.y), scale);
+    }
+  }
+  const int npages = (kv_max + PAGE - 1) / PAGE;
+  for (int pg = 0; pg < npages; ++pg) {
+    const int phys = block_table[pg];
+    const uint4* ksrc = reinterpret_cast<const uint4*>(kv_pool + (((size_t)phys * 2 + 0) * n_kv + kvh) * (PAGE * HD));
+    const uint4* vsrc = reinterpret_cast<const uint4*>(kv_pool + (((size_t)phys * 2 + 1) * n_kv + kvh) * (PAGE * HD));
+    const int ntok = min(PAGE, kv_max - pg * PAGE);
+    for (int i = threadIdx.x; i < ntok * HD / 8; i += G * 32) {
+      reinterpret_cast<uint4*>(Ks)[i] = ksrc[i];
+      reinterpret_cast<uint4*>(Vs)[i] = vsrc[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+      if (qi >= nq) continue;
+      const int kv_len = pos0 + t0 + qi + 1;              // causal: query t sees positions <= pos0 + t
+      const int vis = min(ntok, kv_len - pg * PAGE);
+      if (vis <= 0) continue;
+#pragma unroll 1
+      for (int h0 = 0; h0 < vis; h0 += 32) {
+        const int nt = min(32, vis - h0);
+        float sc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sc[j] = 0.f;
+          if (j < nt) {
+            const uint2 u = *reinterpret_cast<const uint2*>(Ks + (h0 + j) * HD + lane * 4);
+            sc[j] = fmaf(qv[qi][0], bf_lo(u.x), fmaf(qv[qi][1], bf_hi(u.x), fmaf(qv[qi][2], bf_lo(u.y), qv[qi][3] * bf_hi(u.y))));
+          }
+        }
+        transpose_reduce32(sc, lane);
+        const bool valid = lane < nt;
+        const float s = valid ? sc[0] : -INFINITY;
+        const float m_new = fmaxf(m[qi], warp_max(s));
+        const float pj = valid ? exp2f((s - m_new) * LOG2E) : 0.f;
+        const float corr = exp2f((m[qi] - m_new) * LOG2E);
+        l[qi] = l[qi] * corr + warp_sum(pj);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) o[qi][dd] *= corr;
+        m[qi] = m_new;
+        ps[warp][lane] = pj;
+        __syncwarp();
+        for (int j = 0; j < nt; ++j) {
+          const float pw = ps[warp][j];
+          const uint2 u = *reinterpret_cast<const uint2*>(Vs + (h0 + j) * HD + lane * 4);
+          o[qi][0] = fmaf(pw, bf_lo(u.x), o[qi][0]); o[qi][1] = fmaf(pw, bf_hi(u.x), o[qi][1]);
+          o[qi][2] = fmaf(pw, bf_lo(u.y), o[qi][2]); o[qi][3] = fmaf(pw, bf_hi(u.y), o[qi][3]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int qi = 0; qi < QT; ++qi) {
+    if (qi >= nq) continue;
+    const float invL = 1.0f / l[qi];
+    __align__(8) bf16 ob[4];
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(o[qi][dd] * invL);
+    *reinterpret_cast<uint2*>(out + (size_t)(t0 + qi) * n_heads * HD + head * HD + lane * 4) = *reinterpret_cast<const uint2*>(ob);
+  }
+}
+
+}  // namespace dn

@@ -92,7 +92,8 @@ int dn_unbind_layer(dn_model* m, int abs_layer);
 int dn_layer_is_bound(dn_model* m, int abs_layer);
 /* embed_tokens / final norm / lm_head (reference shard/runtime.py:263-273); any may be NULL */
 int dn_bind_api(dn_model* m, const void* embed, const void* norm, const void* head);
-int dn_model_max_chunk(dn_model* m);             /* largest T accepted by dn_layer_forward */
+int dn_model_max_chunk(dn_model* m);             /* largest small chunk (1,2,4) accepted by dn_layer_forward */
+int dn_model_max_prefill_chunk(dn_model* m);     /* 16..this many tokens run on the tcgen05/TMA prefill GEMMs (0: none) */
 
 /* ---- per-nonce KV: replaces make_cache + mlx_lm KVCache
  *      (reference utils/model.py:470-555, shard/runtime.py:374-396) */

@@ -406,3 +406,43 @@ def test_full_size_llama3_8b_dims_two_layers(cuda_lib):
     finally:
         a.unload_model_core()
         b.unload_model_core()
+
+
+def test_tensor_core_prefill_matches_gemv_prefill(tiny, cuda_lib):
+    """The tcgen05/TMA prefill path (chunks of 16..128 tokens) against the GEMV chunk path and the
+    oracle on a 45-token prompt: same greedy continuation, logits inside the bf16 envelope."""
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+    g, w = tiny
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+    prompt = np.random.Generator(np.random.PCG64(5)).integers(0, cfgd["vocab_size"], size=45).tolist()
+    outs = {}
+    for tc in (1, 0):
+        cuda_lib.dn_set_option(b"tc_prefill", tc)
+        rt = make_runtime(cfgd, w, range(L))
+        try:
+            assert rt.model.max_prefill_chunk == (128 if tc else 0)
+            rt.policy.process(token_message(rt, "p", prompt))
+            res = rt.activation_send_queue.get_nowait()
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce["p"].x_view(len(prompt)))
+            torch.cuda.synchronize()
+            toks = [res.token_id]
+            for _ in range(6):
+                rt.policy.process(token_message(rt, "p", [toks[-1]]))
+                toks.append(rt.activation_send_queue.get_nowait().token_id)
+            outs[tc] = (toks, f32.cpu())
+            assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+        finally:
+            rt.unload_model_core()
+    cuda_lib.dn_set_option(b"tc_prefill", 1)
+    orc = LlamaOracle(OracleConfig.from_dict(cfgd), w, exact_linear=True)
+    kv = {l: OracleKV() for l in range(L)}
+    x = orc.embed(torch.tensor(prompt, dtype=torch.int32))
+    for l in range(L):
+        x = orc.apply_single_layer(l, x, kv[l])
+    ref = orc.lm_project(orc.normalize(x[-1:]), return_fp32=True)[0]
+    for tc in (1, 0):
+        assert rel_inf(outs[tc][1], ref) <= max(e2e_tol(g), 5e-3), (tc, rel_inf(outs[tc][1], ref))
+    top2 = torch.topk(ref, 2).values
+    if float(top2[0] - top2[1]) > 0.05:
+        assert outs[1][0][0] == outs[0][0][0] == int(torch.argmax(ref))
