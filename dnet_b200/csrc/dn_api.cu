@@ -136,7 +136,7 @@ struct dn_model {
   bf16 *xa = nullptr, *xb = nullptr;
   // tensor-core prefill scratch ([TPF_MAX][...]) and the TMA descriptors of the activation buffers
   bf16 *pf_xn = nullptr, *pf_qkv = nullptr, *pf_q = nullptr, *pf_attn = nullptr, *pf_h = nullptr, *pf_act = nullptr;
-  CUtensorMap tm_xn64, tm_xn128, tm_attn64, tm_attn128, tm_act64, tm_act128;
+  CUtensorMap tm_xn[3], tm_attn[3], tm_act[3];   // token-tile boxes of 32 / 64 / 128 rows
   bool pf_ok = false;
   unsigned long long* mk_dbg = nullptr;
   size_t mk_dbg_words = 0;
@@ -324,9 +324,13 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
     CK(cudaMemset(m->pf_attn, 0, (size_t)TPF_MAX * qd * 2));
     CK(cudaMemset(m->pf_act, 0, (size_t)TPF_MAX * cfg->ffn * 2));
     m->pf_ok = (H % 128 == 0) && (qd % 128 == 0) && (cfg->ffn % 128 == 0) && ((cfg->n_kv_heads * HD) % 128 == 0) &&
-               make_tmap(&m->tm_xn64, m->pf_xn, TPF_MAX, H, 64) == DN_OK && make_tmap(&m->tm_xn128, m->pf_xn, TPF_MAX, H, 128) == DN_OK &&
-               make_tmap(&m->tm_attn64, m->pf_attn, TPF_MAX, qd, 64) == DN_OK && make_tmap(&m->tm_attn128, m->pf_attn, TPF_MAX, qd, 128) == DN_OK &&
-               make_tmap(&m->tm_act64, m->pf_act, TPF_MAX, cfg->ffn, 64) == DN_OK && make_tmap(&m->tm_act128, m->pf_act, TPF_MAX, cfg->ffn, 128) == DN_OK;
+               true;
+    for (int b = 0; b < 3 && m->pf_ok; ++b) {
+      const int box = 32 << b;
+      m->pf_ok = make_tmap(&m->tm_xn[b], m->pf_xn, TPF_MAX, H, box) == DN_OK &&
+                 make_tmap(&m->tm_attn[b], m->pf_attn, TPF_MAX, qd, box) == DN_OK &&
+                 make_tmap(&m->tm_act[b], m->pf_act, TPF_MAX, cfg->ffn, box) == DN_OK;
+    }
   }
   *out = m;
   return DN_OK;
@@ -537,11 +541,17 @@ static cudaError_t launch_tc(const CUtensorMap& w, const CUtensorMap& w2, const 
   k_gemm_tc<BN, EPI, STAGES><<<grid, TC_THREADS, smem, s>>>(w, w2, x, p);
   return cudaGetLastError();
 }
+// token-tile width: the widest tile that still yields >= ~100 CTAs (a 4096-row matrix has only 32
+// row tiles; narrower token tiles re-read W from L2, not from HBM -- concurrent CTAs share the tile)
 template <int EPI>
-static cudaError_t gemm_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap& x64, const CUtensorMap& x128,
+static cudaError_t gemm_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap* x /*[3]: 32,64,128*/,
                            const TcParams& p, cudaStream_t s) {
-  if (p.T <= 64) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x64, p, s);
-  return launch_tc<128, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x128, p, s);
+  const int n_tiles = (p.N + TC_BM - 1) / TC_BM;
+  auto tiles = [&](int bn) { return n_tiles * ((p.T + bn - 1) / bn); };
+  if (p.T > 64 && tiles(128) >= 100) return launch_tc<128, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x[2], p, s);
+  if (p.T > 32 && tiles(64) >= 100) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 5 : 8)>(w, w2, x[1], p, s);
+  if (p.T > 32 && tiles(32) < 100 && tiles(64) * 2 > tiles(32)) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 5 : 8)>(w, w2, x[1], p, s);
+  return launch_tc<32, EPI, (EPI == EPI_SWIGLU ? 5 : 8)>(w, w2, x[0], p, s);
 }
 
 static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, cudaStream_t s) {
@@ -562,11 +572,11 @@ static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* k
   g_launches++;
   p.K = H; p.Y = m->pf_qkv; p.ldy = qkvd;
   p.N = qd; p.col0 = 0; p.bias = L.w[DN_W_QB];
-  CK(gemm_tc<EPI_STORE>(L.tm[0], L.tm[0], m->tm_xn64, m->tm_xn128, p, s));
+  CK(gemm_tc<EPI_STORE>(L.tm[0], L.tm[0], m->tm_xn, p, s));
   p.N = kd; p.col0 = qd; p.bias = L.w[DN_W_KB];
-  CK(gemm_tc<EPI_STORE>(L.tm[1], L.tm[1], m->tm_xn64, m->tm_xn128, p, s));
+  CK(gemm_tc<EPI_STORE>(L.tm[1], L.tm[1], m->tm_xn, p, s));
   p.col0 = qd + kd; p.bias = L.w[DN_W_VB];
-  CK(gemm_tc<EPI_STORE>(L.tm[2], L.tm[2], m->tm_xn64, m->tm_xn128, p, s));
+  CK(gemm_tc<EPI_STORE>(L.tm[2], L.tm[2], m->tm_xn, p, s));
   p.bias = nullptr;
   k_rope_append<<<dim3(c.n_heads + 2 * c.n_kv_heads, T), 128, 0, s>>>(m->pf_qkv, m->pf_q, pool, kv->block_table, kv->st, m->inv_freq,
                                                                         c.n_heads, c.n_kv_heads);
@@ -579,13 +589,13 @@ static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* k
     g_launches++;
   }
   p.K = qd; p.N = H; p.Y = m->pf_h; p.ldy = H; p.col0 = 0; p.resid = x; p.ldr = H;
-  CK(gemm_tc<EPI_RESID>(L.tm[3], L.tm[3], m->tm_attn64, m->tm_attn128, p, s));
+  CK(gemm_tc<EPI_RESID>(L.tm[3], L.tm[3], m->tm_attn, p, s));
   k_rmsnorm_rows<<<T, 256, 0, s>>>(m->pf_h, L.w[DN_W_LN2], m->pf_xn, H, c.rms_eps);
   g_launches++;
   p.K = H; p.N = c.ffn; p.Y = m->pf_act; p.ldy = c.ffn; p.resid = nullptr;
-  CK(gemm_tc<EPI_SWIGLU>(L.tm[4], L.tm[5], m->tm_xn64, m->tm_xn128, p, s));
+  CK(gemm_tc<EPI_SWIGLU>(L.tm[4], L.tm[5], m->tm_xn, p, s));
   p.K = c.ffn; p.N = H; p.Y = x; p.ldy = H; p.resid = m->pf_h; p.ldr = H;
-  CK(gemm_tc<EPI_RESID>(L.tm[6], L.tm[6], m->tm_act64, m->tm_act128, p, s));
+  CK(gemm_tc<EPI_RESID>(L.tm[6], L.tm[6], m->tm_act, p, s));
   CK(cudaGetLastError());
   return DN_OK;
 }

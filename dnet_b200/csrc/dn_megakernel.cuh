@@ -175,8 +175,10 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int 
     }
     __threadfence();
   } else if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p.bar_count, 1u);
+    // release-arrive / acquire-poll: the CTA barrier above orders every consumer thread's writes
+    // before this release (cumulativity), the one below orders their reads after the acquire.
+    // Cross-CTA activations are read with ld.global.cg (L2), so no L1 invalidation is needed.
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
     const unsigned int target = base + (k + 1u) * gridDim.x;
     if ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
       const unsigned long long t0 = gtimer();
@@ -188,7 +190,6 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int 
         }
       }
     }
-    __threadfence();
   }
   k += 1u;
   cbar_sync();

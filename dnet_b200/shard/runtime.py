@@ -125,6 +125,7 @@ class ShardRuntime:
         self._mlx_lock = threading.Lock()  # name kept for drop-in parity; guards C-ABI calls
         self._model_lock = threading.Lock()
         self._kv_by_nonce: Dict[str, NonceState] = {}
+        self._ns_pool: List[NonceState] = []     # recycled nonce states: creating one costs cudaMalloc + pinned alloc
         self._kv_last_seen: Dict[str, float] = {}
         self._kv_ttl_s: float = self.kv_cache_config.kv_ttl_s
         # CUDA plumbing
@@ -168,9 +169,10 @@ class ShardRuntime:
                 pass
             self.compute_thread = None
         self.executor.shutdown(wait=True, cancel_futures=True)
-        for ns in self._kv_by_nonce.values():
+        for ns in list(self._kv_by_nonce.values()) + self._ns_pool:
             ns.free()
         self._kv_by_nonce.clear()
+        self._ns_pool.clear()
         self._kv_last_seen.clear()
 
     # -- model load ------------------------------------------------------------------------
@@ -251,9 +253,10 @@ class ShardRuntime:
                         break
                 if self.compute_stream is not None:
                     self.compute_stream.synchronize()
-                for ns in self._kv_by_nonce.values():
+                for ns in list(self._kv_by_nonce.values()) + self._ns_pool:
                     ns.free()
                 self._kv_by_nonce.clear()
+                self._ns_pool.clear()
                 self._kv_last_seen.clear()
                 self.policy.clear()
                 self.policy = NoopPolicy(runtime=self, resident_windows=1)
@@ -311,15 +314,34 @@ class ShardRuntime:
                 self._kv_last_seen.pop(n, None)
                 old = self._kv_by_nonce.pop(n, None)
                 if old is not None:
-                    if self.compute_stream is not None:
-                        self.compute_stream.synchronize()
-                    old.free()
+                    self._recycle(old)
         ns = self._kv_by_nonce.get(nonce)
         if ns is None:
-            ns = NonceState(self.model, self.kv_cache_config.max_tokens)
+            if self._ns_pool:
+                ns = self._ns_pool.pop()
+                ns.kv.reset(self.compute_stream_ptr)
+            else:
+                ns = NonceState(self.model, self.kv_cache_config.max_tokens)
             self._kv_by_nonce[nonce] = ns
         self._kv_last_seen[nonce] = time.perf_counter()
         return ns
+
+    def _recycle(self, ns: NonceState) -> None:
+        """An expired nonce's KV pages, buffers and pinned result are kept for the next nonce."""
+        if ns.kv.max_tokens >= self.kv_cache_config.max_tokens and len(self._ns_pool) < 64:
+            ns.drop_graphs()
+            self._ns_pool.append(ns)
+        else:
+            if self.compute_stream is not None:
+                self.compute_stream.synchronize()
+            ns.free()
+
+    def release_nonce(self, nonce: str) -> None:
+        """Explicit end-of-request (the reference only has the TTL sweep)."""
+        ns = self._kv_by_nonce.pop(nonce, None)
+        self._kv_last_seen.pop(nonce, None)
+        if ns is not None:
+            self._recycle(ns)
 
     def start(self):
         self.running = True
