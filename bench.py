@@ -269,6 +269,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         return rt.activation_send_queue.get_nowait()
     first = prefill("dev")
     torch.cuda.synchronize()
+    if args.megakernel and args.calibrate:
+        from dnet_b200.shard.calibrate import calibrate
+        tcal = time.perf_counter()
+        calibrate(rt)
+        log(f"step-kernel partition calibrated in {time.perf_counter() - tcal:.2f}s")
     log(f"model ready + prefill in {time.perf_counter() - t0:.1f}s; first token {first.token_id} lp {first.logprob}")
     run = list(range(L))
     stream = rt.compute_stream
@@ -414,6 +419,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "step_kernel": "k_shard_step (one persistent cooperative kernel per token)" if args.megakernel
                    else "per-op kernels replayed as a CUDA graph",
                    "step_error": int(lib.dn_step_error(rt.model._h, rt.compute_stream_ptr)),
+                   "partition": "per-SM calibrated (dnet_b200.shard.calibrate)" if (args.megakernel and args.calibrate) else "equal",
                    "sequences_in_flight": 1},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "check": {"nonce0_token_after_steps": W + K, "token": dev_last_token},
@@ -454,6 +460,7 @@ def main():
     ap.add_argument("--l2-prefetch-kb", type=int, default=64)
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--mk-flags", type=int, default=0)
+    ap.add_argument("--calibrate", type=int, default=1, help="per-SM row-partition calibration of the step kernel")
     ap.add_argument("--fused-hop", type=int, default=1, help="N>1: wait+step+hop in one kernel")
     ap.add_argument("--pf-depth", type=int, default=-1, help="megakernel L2 prefetch look-ahead (ring stages); -1 = library default")
     ap.add_argument("--in-flight", type=int, default=0, help="sequences in flight at N>1 (default N)")

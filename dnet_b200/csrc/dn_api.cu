@@ -140,6 +140,8 @@ struct dn_model {
   bool pf_ok = false;
   unsigned long long* mk_dbg = nullptr;
   size_t mk_dbg_words = 0;
+  int* mk_bounds = nullptr;      // [4][sms+1] calibrated row partition of the step kernel (null: equal split)
+  bool mk_bounds_on = false;
   unsigned int* mk_sync = nullptr;   // [0] barrier count, [1] generation, [2] error, [3] head ticket
 };
 
@@ -340,7 +342,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   if (!m) return DN_OK;
   cudaFree(m->hbuf); cudaFree(m->qbuf); cudaFree(m->attn); cudaFree(m->act); cudaFree(m->logits_bf16);
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
-  cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
+  cudaFree(m->mk_bounds); cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
   cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
   delete m;
   return DN_OK;
@@ -802,6 +804,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
   p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;
+  p.bounds = m->mk_bounds_on ? m->mk_bounds : nullptr;
   p.dbg = nullptr;
   if (g_mk_debug) {
     const size_t words = (size_t)g_sms * (n > 0 ? n : 1) * 16;
@@ -852,6 +855,31 @@ extern "C" int dn_step_debug(dn_model* m, unsigned long long* out_host, size_t m
   CK(cudaMemcpyAsync(out_host, m->mk_dbg, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)s));
   CK(cudaStreamSynchronize((cudaStream_t)s));
   return (int)(n / 16);
+}
+
+// Row partition of the four weight phases of k_shard_step over the SMs: bounds_host is
+// [4][sms+1] (QKV, O, GATE/UP, DOWN), non-decreasing, bounds[ph][0] = 0, bounds[ph][sms] = rows of the
+// phase (virtual rows: pairs interleaved for QKV and GATE/UP, so entries must be even there).
+// Used to give faster SMs proportionally more rows (measured with option mk_debug); results do not
+// depend on the partition (each output row has a fixed summation order).  NULL restores the equal split.
+extern "C" int dn_step_set_bounds(dn_model* m, const int32_t* bounds_host) {
+  if (!m) return fail(DN_EINVAL, "null model");
+  if (!bounds_host) { m->mk_bounds_on = false; return DN_OK; }
+  const dn_model_cfg& c = m->cfg;
+  const int rows[4] = {(c.n_heads + 2 * c.n_kv_heads) * HD, c.hidden, 2 * c.ffn, c.hidden};
+  const int align[4] = {2, 1, 2, 1};
+  const int n = g_sms + 1;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int32_t* b = bounds_host + ph * n;
+    if (b[0] != 0 || b[g_sms] != rows[ph]) return fail(DN_EINVAL, "bounds of phase %d must span [0, %d]", ph, rows[ph]);
+    for (int i = 0; i < g_sms; ++i)
+      if (b[i + 1] < b[i] || (b[i] % align[ph])) return fail(DN_EINVAL, "bounds of phase %d not monotone / aligned at %d", ph, i);
+  }
+  if (!m->mk_bounds) CK(cudaMalloc(&m->mk_bounds, (size_t)4 * n * sizeof(int)));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(m->mk_bounds, bounds_host, (size_t)4 * n * sizeof(int), cudaMemcpyHostToDevice));
+  m->mk_bounds_on = true;
+  return DN_OK;
 }
 
 // 0 = clean; 2/3 = a bounded spin inside k_shard_step timed out (results of that step are invalid)

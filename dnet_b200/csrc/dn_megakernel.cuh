@@ -75,6 +75,7 @@ struct MkParams {
   const uint32_t* wait_flag; uint32_t wait_seq;
   const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
   void* send_dst; uint32_t* send_flag; uint32_t send_seq;
+  const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
 };
@@ -230,7 +231,12 @@ __device__ __forceinline__ const bf16* mk_row(const MkParams& p, const MkLayer& 
     default: return p.head_w + (size_t)vr * K;
   }
 }
-__device__ __forceinline__ void mk_range(const MkPhase& d, int& r0, int& r1) {
+__device__ __forceinline__ void mk_range(const MkParams& p, int ph, const MkPhase& d, int& r0, int& r1) {
+  if (p.bounds != nullptr && ph < PH_HEAD) {     // per-SM calibrated partition (dn_step_set_bounds)
+    r0 = p.bounds[ph * (gridDim.x + 1) + blockIdx.x];
+    r1 = p.bounds[ph * (gridDim.x + 1) + blockIdx.x + 1];
+    return;
+  }
   const int units = d.nrows / d.align;
   r0 = (int)(((long long)units * blockIdx.x) / gridDim.x) * d.align;
   r1 = (int)(((long long)units * (blockIdx.x + 1)) / gridDim.x) * d.align;
@@ -260,7 +266,7 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
   const uint64_t pol = l2_policy_evict_first();
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
-  mk_range(d, r0, r1);
+  mk_range(p, ph, d, r0, r1);
   const int nseg = d.K / d.seg;
   const uint32_t rowbytes = (uint32_t)d.seg * 2u;
   for (int rb = r0; rb < r1; rb += MK_ROWS) {
@@ -303,7 +309,7 @@ __device__ __forceinline__ void mk_prefetch_phase(const MkParams& p, const MkLay
   const uint64_t pol = l2_policy_evict_last();
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
-  mk_range(d, r0, r1);
+  mk_range(p, ph, d, r0, r1);
   // One prefetch op covers up to 8 KiB of a row (4 ring stages), not one 2 KiB segment: the TMA
   // unit retires ~1 bulk op per 46 cycles whatever its size, and a prefetch per segment doubles
   // the op count (measured: look-ahead >= 16 stages dropped the step to 4.9 ms).
@@ -354,7 +360,7 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ri
                                            volatile unsigned int* consumed, unsigned int& ncons, Epi epi) {
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
-  mk_range(d, r0, r1);
+  mk_range(p, ph, d, r0, r1);
   const int nseg = d.K / d.seg;
   const int nch = d.seg >> 8;
   const int rowbytes = d.seg * 2;

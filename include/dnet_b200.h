@@ -136,6 +136,9 @@ int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, void* x_ino
                       const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
                       void* send_dst, uint32_t* send_flag, uint32_t send_seq, dn_stream s);
 int dn_step_error(dn_model* m, dn_stream s);
+/* per-SM row partition of the step kernel's four weight phases, [4][sms+1] (NULL: equal split); see
+ * dnet_b200.shard.calibrate */
+int dn_step_set_bounds(dn_model* m, const int32_t* bounds_host);
 /* measurement hook: per-phase globaltimer stamps [sm][layer][16] of the last step (option mk_debug=1) */
 int dn_step_debug(dn_model* m, unsigned long long* out_host, size_t max_words, dn_stream s);      /* 0, or the code of a timed-out in-kernel wait */
 /* measurement hooks for bench.py: per-kernel device times (CUDA events on stream s between

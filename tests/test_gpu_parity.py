@@ -446,3 +446,43 @@ def test_tensor_core_prefill_matches_gemv_prefill(tiny, cuda_lib):
     top2 = torch.topk(ref, 2).values
     if float(top2[0] - top2[1]) > 0.05:
         assert outs[1][0][0] == outs[0][0][0] == int(torch.argmax(ref))
+
+
+def test_calibrated_partition_does_not_change_results(tiny, cuda_lib):
+    """dn_step_set_bounds re-partitions rows over SMs; every output row keeps its summation order,
+    so tokens, logprobs and logits must stay bit-identical."""
+    import ctypes as C
+    from dnet_b200.shard.calibrate import calibrate
+    g, w = tiny
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+    base = None
+    for cal in (False, True):
+        rt = make_runtime(cfgd, w, range(L), megakernel=True)
+        try:
+            if cal:
+                b = calibrate(rt, rounds=2)
+                assert all(int(x[-1]) > 0 and (np.diff(x) >= 0).all() for x in b)
+                # a deliberately skewed (but valid) partition must not change anything either
+                sms = cuda_lib.dn_device_sm_count()
+                rows = [(cfgd["num_attention_heads"] + 2 * cfgd["num_key_value_heads"]) * 128, cfgd["hidden_size"],
+                        2 * cfgd["intermediate_size"], cfgd["hidden_size"]]
+                tbl = []
+                for r, al in zip(rows, (2, 1, 2, 1)):
+                    units = r // al
+                    cuts = np.minimum(units, (np.arange(sms + 1) ** 2 * units) // (sms * sms)) * al
+                    cuts[-1] = r
+                    tbl.append(cuts)
+                t32 = np.concatenate(tbl).astype(np.int32)
+                assert cuda_lib.dn_step_set_bounds(rt.model._h, t32.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+            out = ring_generate([rt], "n0", g["prompt"].tolist(), 8)
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce["n0"].x1)
+            torch.cuda.synchronize()
+            cur = ([t for t, _, _ in out], [p for _, p, _ in out], f32.cpu())
+            assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+            if base is None:
+                base = cur
+            else:
+                assert cur[0] == base[0] == g["tokens"][:8].tolist() and cur[1] == base[1] and torch.equal(cur[2], base[2])
+        finally:
+            rt.unload_model_core()

@@ -21,6 +21,10 @@ prompt = torch.randint(0, cfg["vocab_size"], (128,), generator=g).tolist()
 pol.process(token_message(rt, "d", prompt)); first = rt.activation_send_queue.get_nowait()
 ns = rt.get_or_make_kv("d"); ns.kv.set_token(first.token_id, rt.compute_stream_ptr)
 run = list(range(L))
+if int(os.environ.get("CALIB", "0")):
+    from dnet_b200.shard.calibrate import calibrate
+    b = calibrate(rt)
+    print("calibrated; gu rows per SM min/max", int(np.diff(b[2]).min()), int(np.diff(b[2]).max()))
 for _ in range(5): pol._graph_step(ns, ns.x1, True, run, True)
 lib.dn_set_option(b"mk_debug", 1)
 pol._graph_step(ns, ns.x1, True, run, True)
