@@ -486,3 +486,40 @@ def test_calibrated_partition_does_not_change_results(tiny, cuda_lib):
                 assert cur[0] == base[0] == g["tokens"][:8].tolist() and cur[1] == base[1] and torch.equal(cur[2], base[2])
         finally:
             rt.unload_model_core()
+
+
+@pytest.mark.parametrize("plen", [1, 2, 3, 15, 16, 17, 33, 63, 64, 65, 127, 128, 129, 200])
+def test_prompt_length_edges_against_oracle(tiny, cuda_lib, plen):
+    """Ragged prompt lengths around every chunking boundary (GEMV chunks of 1/2/4, tensor-core chunks
+    of 16..128 with 32/64/128-token tiles and out-of-bounds token rows, 64-token KV pages): prefill
+    logits vs the oracle on the same prompt, then two decode steps that read the KV it wrote."""
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+    g, w = tiny
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+    prompt = np.random.Generator(np.random.PCG64([plen, 9])).integers(0, cfgd["vocab_size"], size=plen).tolist()
+    orc = LlamaOracle(OracleConfig.from_dict(cfgd), w, exact_linear=True)
+    kv = {l: OracleKV() for l in range(L)}
+    rt = make_runtime(cfgd, w, range(L), max_tokens=256)
+    try:
+        ids = prompt
+        for step in range(3):
+            rt.policy.process(token_message(rt, "e", ids))
+            res = rt.activation_send_queue.get_nowait()
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce["e"].x_view(len(ids)))
+            torch.cuda.synchronize()
+            x = orc.embed(torch.tensor(ids, dtype=torch.int32))
+            for l in range(L):
+                x = orc.apply_single_layer(l, x, kv[l])
+            ref = orc.lm_project(orc.normalize(x[-1:]), return_fp32=True)[0]
+            r = rel_inf(f32.cpu(), ref)
+            assert r <= max(e2e_tol(g), 5e-3), f"plen {plen} step {step}: rel {r}"
+            top2 = torch.topk(ref, 2).values
+            tok_ref = int(torch.argmax(ref.to(torch.bfloat16).float()))
+            if float(top2[0] - top2[1]) > 4 * 2.0 ** -8 * float(top2[0].abs()):
+                assert res.token_id == tok_ref
+            ids = [tok_ref]                       # teacher-force the oracle's token on both sides
+        assert rt._kv_by_nonce["e"].kv.offset == plen + 2
+        assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+    finally:
+        rt.unload_model_core()
