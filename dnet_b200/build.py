@@ -8,7 +8,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 SRC = ROOT / "csrc" / "dn_api.cu"
-DEPS = [SRC, ROOT / "csrc" / "dn_kernels.cuh", ROOT.parent / "include" / "dnet_b200.h"]
+DEPS = [*sorted((ROOT / "csrc").glob("*.cu*")), ROOT.parent / "include" / "dnet_b200.h"]
 OUT = ROOT / "lib" / "libdnet_b200.so"
 
 NVCC_FLAGS = [

@@ -40,6 +40,7 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
+static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
 static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
                               // harmful beyond -- 148 SMs x depth x 32 KB must stay well inside one L2 partition)
@@ -244,6 +245,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
+  if (!strcmp(key, "attn_chunk")) { g_attn_chunk = value < 32 ? 32 : (int)((value + 31) / 32 * 32); return DN_OK; }
   if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
   if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
   return fail(DN_EINVAL, "unknown option '%s'", key);
@@ -801,13 +803,14 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.token_out = token_out; p.logprob_out = logprob_out; p.do_head = do_head ? 1 : 0; p.advance = advance ? 1 : 0;
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
+  p.attn_chunk = g_attn_chunk;
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
   p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;
   p.bounds = m->mk_bounds_on ? m->mk_bounds : nullptr;
   p.dbg = nullptr;
   if (g_mk_debug) {
-    const size_t words = (size_t)g_sms * (n > 0 ? n : 1) * 16;
+    const size_t words = (size_t)g_sms * (n > 0 ? n : 1) * dn::MK_DBG_WORDS;
     if (m->mk_dbg_words < words) {
       cudaFree(m->mk_dbg);
       CK(cudaMalloc(&m->mk_dbg, words * 8));
@@ -818,13 +821,13 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.bar_gen = m->mk_sync + 4;
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
-  const int attn_bytes = 2 * PAGE * HD * 2 + 8 * 32 * 4 + 64;
+  const int attn_bytes = 8 * 132 * 4 + 64;                 // per-warp attention partials
   if (scratch < attn_bytes) scratch = attn_bytes;
   const int merge_bytes = c.n_heads * HD * 2 + c.n_heads * m->nsplit * 8 + 64;   // o_proj vector + (m,l) table
   if (scratch < merge_bytes) scratch = merge_bytes;
   if (c.hidden > 8192) return fail(DN_EINVAL, "hidden > 8192 unsupported by the step kernel's RMSNorm staging");
   scratch = (scratch + 1023) / 1024 * 1024;
-  const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4;
+  const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4 + 128 * 4;   // barriers, misc scratch, RoPE table
   int stages = (227 * 1024 - scratch - tail) / MK_STAGE_BYTES;
   if (stages > MK_MAX_STAGES) stages = MK_MAX_STAGES;
   if (stages < 2) return fail(DN_EINVAL, "model too wide for the megakernel's shared-memory ring");

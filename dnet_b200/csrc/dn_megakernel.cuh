@@ -27,13 +27,20 @@ namespace dn {
 constexpr int MK_CW = 8;                        // consumer warps
 constexpr int MK_CTHREADS = MK_CW * 32;         // 256
 constexpr int MK_PW = 2;                        // producer warps (alternate ring stages)
-constexpr int MK_THREADS = MK_CTHREADS + (MK_PW + 1) * 32;   // + producers + L2 prefetch warp
+constexpr int MK_THREADS = MK_CTHREADS + 4 * 32;   // + one warpgroup: 2 producers, the L2 prefetch warp, 1 idle warp
+// register re-allocation (setmaxnreg works per warpgroup): the data-movement warpgroup gives most
+// of its registers to the 8 consumer warps.  8*32*224 + 4*32*56 = 64512 <= 65536
+constexpr int MK_REGS_CONSUMER = 224, MK_REGS_PRODUCER = 56;
 constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
 constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
 constexpr int MK_STAGE_BYTES = MK_ROWS * MK_MAX_SEG * 2;   // 32 KB
 constexpr int MK_MAX_STAGES = 8;
 // r01 measurement: with 512-byte bulk copies the step ran at 2.2 TB/s (one TMA op per ~66
 // cycles per SM is the limit, not bytes), so a stage is 16 rows x 1024 columns = 16 ops of 2 KiB.
+#ifndef MK_OPT_PRE
+#define MK_OPT_PRE 1   // issue the epilogue's residual load before the row block's stages
+#endif
+constexpr int MK_DBG_WORDS = 32;   // per (CTA, layer): 15 phase stamps, [16..19] producer-blocked ns, [24..27] consumer-wait ns
 constexpr unsigned long long MK_TIMEOUT_NS = 4000000000ull;  // bounded spins
 
 enum { MK_W_Q = 0, MK_W_K, MK_W_V, MK_W_O, MK_W_GATE, MK_W_UP, MK_W_DOWN, MK_W_LN1, MK_W_LN2, MK_W_QB, MK_W_KB, MK_W_VB, MK_W_N };
@@ -75,6 +82,7 @@ struct MkParams {
   const uint32_t* wait_flag; uint32_t wait_seq;
   const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
   void* send_dst; uint32_t* send_flag; uint32_t send_seq;
+  int attn_chunk;            // minimum tokens per attention split (multiple of 32)
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
@@ -120,6 +128,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
       return;
     }
   }
+}
+// debug variant: also accumulates the time spent waiting into *acc_ns (mk_debug only)
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned long long* acc_ns) {
+  if (acc_ns == nullptr) { mbar_wait(bar, parity, err); return; }
+  {   // test_wait never suspends (try_wait may block for a hardware time slice and hide the wait)
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  const unsigned long long t0 = gtimer();
+  mbar_wait(bar, parity, err);
+  *acc_ns += gtimer() - t0;
 }
 // L2 eviction policies: weights are read exactly once per step, so demand loads are marked
 // evict-first (they must not push KV pages, activations or prefetched tiles out of L2) and
@@ -262,8 +283,10 @@ struct MkRing {
 // share but not for refilling the ring from L2 after a stall).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLayer& L, int ph, MkRing& ring, int lane,
-                                                 int which, unsigned int& idx) {
+                                                 int which, unsigned int& idx, int li) {
   const uint64_t pol = l2_policy_evict_first();
+  unsigned long long stall = 0;
+  unsigned long long* accp = (p.dbg != nullptr && which == 0) ? &stall : nullptr;
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(p, ph, d, r0, r1);
@@ -274,7 +297,7 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
     const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
     for (int sg = 0; sg < nseg; ++sg) {
       if ((int)(idx % MK_PW) == which) {
-        mbar_wait(&ring.empty[ring.stage], ring.phase ^ 1u, p.err);
+        mbar_wait_dbg(&ring.empty[ring.stage], ring.phase ^ 1u, p.err, accp);
         if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * rowbytes);
         __syncwarp();
         if (lane < nv)
@@ -285,19 +308,21 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
       ring.advance();
     }
   }
+  // mk_debug: ns producer 0 spent blocked on a full ring while producing this (layer, phase)
+  if (accp != nullptr && lane == 0 && ph < 4) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * MK_DBG_WORDS + 16 + ph] = stall;
 }
 __device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int lane, int which) {
   unsigned int idx = 0;
   for (int li = 0; li < p.n_layers; ++li) {
     const MkLayer L = p.layers[li];
-    mk_produce_phase(p, L, PH_QKV, ring, lane, which, idx);
-    mk_produce_phase(p, L, PH_O, ring, lane, which, idx);
-    mk_produce_phase(p, L, PH_GU, ring, lane, which, idx);
-    mk_produce_phase(p, L, PH_DOWN, ring, lane, which, idx);
+    mk_produce_phase(p, L, PH_QKV, ring, lane, which, idx, li);
+    mk_produce_phase(p, L, PH_O, ring, lane, which, idx, li);
+    mk_produce_phase(p, L, PH_GU, ring, lane, which, idx, li);
+    mk_produce_phase(p, L, PH_DOWN, ring, lane, which, idx, li);
   }
   if (p.do_head) {
     const MkLayer L0 = p.layers[0];
-    mk_produce_phase(p, L0, PH_HEAD, ring, lane, which, idx);
+    mk_produce_phase(p, L0, PH_HEAD, ring, lane, which, idx, 0);
   }
 }
 
@@ -355,22 +380,28 @@ __device__ __forceinline__ void mk_prefetcher(const MkParams& p, int lane, volat
 // lanes 0 and 16 are the row owners (2 rows per warp per block); the partner row of a
 // RoPE / SwiGLU pair sits 16 lanes away.
 // ---------------------------------------------------------------------------------
-template <class Epi>
-__device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ring, const bf16* xs, int cw, int lane,
-                                           volatile unsigned int* consumed, unsigned int& ncons, Epi epi) {
+template <class Pre, class Epi>
+__device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, MkRing& ring, const bf16* xs, int cw, int lane,
+                                           volatile unsigned int* consumed, unsigned int& ncons, Pre pre, Epi epi) {
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(p, ph, d, r0, r1);
   const int nseg = d.K / d.seg;
   const int nch = d.seg >> 8;
   const int rowbytes = d.seg * 2;
+  unsigned long long waited = 0;
+  unsigned long long* accp = (p.dbg != nullptr && cw == 0) ? &waited : nullptr;
   for (int rb = r0; rb < r1; rb += MK_ROWS) {
     const int nv = min(MK_ROWS, r1 - rb);
     const int myrows = min(2, max(0, nv - 2 * cw));
+    // row-owner lanes issue their epilogue's global loads now, so the round trip hides under the block's stages
+    const int r_own = 2 * cw + ((lane >> 4) & 1);
+    const bool owner_lane = r_own < nv && (lane & 15) == 0;
+    const auto pv = pre(rb + r_own, owner_lane);
     float acc[2] = {0.f, 0.f};
     for (int sg = 0; sg < nseg; ++sg) {
-      mbar_wait(&ring.full[ring.stage], ring.phase, p.err);
-      if (myrows > 0) {
+      mbar_wait_dbg(&ring.full[ring.stage], ring.phase, p.err, accp);
+      if (myrows > 0 && !(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
         const unsigned char* tile = ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)(2 * cw) * rowbytes + lane * 16;
         const bf16* xseg = xs + (size_t)sg * d.seg + (lane << 3);
 #pragma unroll 4
@@ -400,9 +431,10 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, MkRing& ri
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
-    const int r_local = 2 * cw + ((lane >> 4) & 1);
-    epi(rb + r_local, v, r_local < nv && (lane & 15) == 0);
+    epi(rb + r_own, v, owner_lane, pv);
   }
+  // mk_debug: ns consumer warp 0 waited for weights (ring empty = HBM-bound time) in this phase
+  if (accp != nullptr && lane == 0 && ph < 4) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * MK_DBG_WORDS + 24 + ph] = waited;
 }
 
 // stage a bf16 vector [K] from global (produced by other CTAs: bypass L1) into shared memory
@@ -456,93 +488,108 @@ __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const
   cbar_sync();
 }
 
-// attention split geometry shared by the attention phase and the merge: splits are chunks of
-// tokens (multiples of 32), so a short context still spreads over many CTAs
-__device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, int& chunk, int& nact) {
-  int c = (kv_len + p.nsplit - 1) / p.nsplit;
-  c = (c + 31) / 32 * 32;           // 32-token granularity: short contexts -> ~kv_len/32 splits
-  if (c < 32) c = 32;
-  chunk = c;
-  nact = (kv_len + c - 1) / c;
+// attention geometry shared by the attention phase and the o_proj staging.  The context is cut
+// into 32-token tiles; one CTA serves one (q head, CTA split) and its 8 consumer warps take the
+// split's tiles round-robin, merging through shared memory.  A second CTA split per head is only
+// added once every warp already has `attn_chunk` tokens, so short contexts need no cross-CTA
+// merge at all (S == 1: the CTA writes the normalised head output directly).
+__device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, int& S, int& tps) {
+  const int n_tiles = (kv_len + 31) >> 5;
+  int smax = (int)gridDim.x / p.n_heads;
+  smax = max(1, min(smax, min(p.nsplit, 8)));
+  const int per_cta = MK_CW * max(1, p.attn_chunk >> 5);
+  int s = (n_tiles + per_cta - 1) / per_cta;
+  s = max(1, min(s, smax));
+  tps = (n_tiles + s - 1) / s;
+  S = (n_tiles + tps - 1) / tps;
 }
 
 // ---------------------------------------------------------------------------------
-// attention phase for one (kv head, split) task on the 256 consumer threads; warps < G compute
+// attention phase: K and V rows go global -> registers (one 256-byte row per warp-wide load,
+// 32 rows in flight), no shared-memory staging and no CTA-wide sync inside the tile loop
 // ---------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane) {
+__device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane,
+                                             int S, int tps, int tile_first, int phys_first) {
   const int kv_len = p.st->pos + 1;
-  int chunk, nact;
-  mk_attn_geometry(p, kv_len, chunk, nact);
-  const int task = blockIdx.x;
-  if (task >= p.n_kv * nact) return;                  // CTA-uniform
-  const int kvh = task / nact, sp = task % nact;
-  const int t0 = sp * chunk, t1 = min(kv_len, t0 + chunk);
-  bf16* Ks = reinterpret_cast<bf16*>(scratch);
-  bf16* Vs = Ks + PAGE * HD;
-  float* ps = reinterpret_cast<float*>(scratch + 2 * PAGE * HD * sizeof(bf16));   // [G][32]
-  const int head = kvh * G + cw;
+  const int n_tiles = (kv_len + 31) >> 5;
+  float* wpart = reinterpret_cast<float*>(scratch);           // [MK_CW][132]: o[128], m, l per warp
   const float scale = 0.08838834764831845f;
-  float qv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (cw < G) {
-    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(p.qbuf + head * HD + lane * 4));
-    qv[0] = __fmul_rn(bf_lo(u.x), scale); qv[1] = __fmul_rn(bf_hi(u.x), scale);
-    qv[2] = __fmul_rn(bf_lo(u.y), scale); qv[3] = __fmul_rn(bf_hi(u.y), scale);
-  }
-  float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int tt = t0; tt < t1; tt += PAGE) {
-    const int ntok = min(PAGE, t1 - tt);
-    // tile of up to 64 tokens (may straddle a page boundary): one 256-byte K row + V row per token
-    for (int i = threadIdx.x; i < ntok * 16; i += MK_CTHREADS) {
-      const int tok = tt + (i >> 4), part = i & 15;
-      const int phys = p.block_table[tok / PAGE];
-      const size_t base = (((size_t)phys * 2) * p.n_kv + kvh) * (PAGE * HD) + (size_t)(tok % PAGE) * HD;
-      const uint4* ksrc = reinterpret_cast<const uint4*>(L.kv_pool + base);
-      const uint4* vsrc = reinterpret_cast<const uint4*>(L.kv_pool + base + (size_t)p.n_kv * (PAGE * HD));
-      reinterpret_cast<uint4*>(Ks)[i] = __ldcg(ksrc + part);
-      reinterpret_cast<uint4*>(Vs)[i] = __ldcg(vsrc + part);
+  for (int task = blockIdx.x; task < p.n_heads * S; task += gridDim.x) {     // CTA-uniform
+    const int head = task / S, sp = task % S;
+    const int kvh = head / G;
+    const int tile1 = min(n_tiles, (sp + 1) * tps);
+    float qv[4];
+    {
+      const uint2 u = __ldcg(reinterpret_cast<const uint2*>(p.qbuf + head * HD + lane * 4));
+      qv[0] = __fmul_rn(bf_lo(u.x), scale); qv[1] = __fmul_rn(bf_hi(u.x), scale);
+      qv[2] = __fmul_rn(bf_lo(u.y), scale); qv[3] = __fmul_rn(bf_hi(u.y), scale);
     }
-    cbar_sync();
-    if (cw < G) {
+    float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int h0 = 0; h0 < ntok; h0 += 32) {
-        const int nt = min(32, ntok - h0);
-        float sc[32];
+    for (int tile = sp * tps + cw; tile < tile1; tile += MK_CW) {
+      const int t0 = tile << 5;
+      const int nt = min(32, kv_len - t0);
+      // a 32-token tile never straddles a 64-token page; the first tile's page was looked up at kernel start
+      const int phys = (task == (int)blockIdx.x && tile == tile_first) ? phys_first : p.block_table[t0 / PAGE];
+      const bf16* kbase = L.kv_pool + (((size_t)phys * 2) * p.n_kv + kvh) * (PAGE * HD) + (size_t)(t0 % PAGE) * HD + lane * 4;
+      const bf16* vbase = kbase + (size_t)p.n_kv * (PAGE * HD);
+      float sc[32];
+      uint2 kr[32], vr[32];                                     // 64 independent 8-byte loads in flight per lane
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          sc[j] = 0.f;
-          if (j < nt) {
-            const uint2 u = *reinterpret_cast<const uint2*>(Ks + (h0 + j) * HD + lane * 4);
-            sc[j] = fmaf(qv[0], bf_lo(u.x), fmaf(qv[1], bf_hi(u.x), fmaf(qv[2], bf_lo(u.y), qv[3] * bf_hi(u.y))));
-          }
-        }
-        transpose_reduce32(sc, lane);
-        const bool valid = lane < nt;
-        const float s = valid ? sc[0] : -INFINITY;
-        const float m_new = fmaxf(m, warp_max(s));
-        const float pj = valid ? exp2f((s - m_new) * LOG2E) : 0.f;
-        const float corr = exp2f((m - m_new) * LOG2E);
-        l = l * corr + warp_sum(pj);
+      for (int j = 0; j < 32; ++j)
+        kr[j] = (j < nt) ? __ldcg(reinterpret_cast<const uint2*>(kbase + j * HD)) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int dd = 0; dd < 4; ++dd) o[dd] *= corr;
-        m = m_new;
-        ps[cw * 32 + lane] = pj;
-        __syncwarp();
-        for (int j = 0; j < nt; ++j) {
-          const float pw = ps[cw * 32 + j];
-          const uint2 u = *reinterpret_cast<const uint2*>(Vs + (h0 + j) * HD + lane * 4);
-          o[0] = fmaf(pw, bf_lo(u.x), o[0]); o[1] = fmaf(pw, bf_hi(u.x), o[1]);
-          o[2] = fmaf(pw, bf_lo(u.y), o[2]); o[3] = fmaf(pw, bf_hi(u.y), o[3]);
+      for (int j = 0; j < 32; ++j)
+        vr[j] = (j < nt) ? __ldcg(reinterpret_cast<const uint2*>(vbase + j * HD)) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        sc[j] = fmaf(qv[0], bf_lo(kr[j].x), fmaf(qv[1], bf_hi(kr[j].x), fmaf(qv[2], bf_lo(kr[j].y), qv[3] * bf_hi(kr[j].y))));
+      transpose_reduce32(sc, lane);
+      const bool valid = lane < nt;
+      const float s = valid ? sc[0] : -INFINITY;
+      const float m_new = fmaxf(m, warp_max(s));
+      const float pj = valid ? exp2f((s - m_new) * LOG2E) : 0.f;
+      const float corr = exp2f((m - m_new) * LOG2E);
+      l = l * corr + warp_sum(pj);
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) o[dd] *= corr;
+      m = m_new;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pw = __shfl_sync(0xffffffffu, pj, j);
+        o[0] = fmaf(pw, bf_lo(vr[j].x), o[0]); o[1] = fmaf(pw, bf_hi(vr[j].x), o[1]);
+        o[2] = fmaf(pw, bf_lo(vr[j].y), o[2]); o[3] = fmaf(pw, bf_hi(vr[j].y), o[3]);
+      }
+    }
+    *reinterpret_cast<float4*>(wpart + cw * 132 + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lane == 0) { wpart[cw * 132 + 128] = m; wpart[cw * 132 + 129] = l; }
+    cbar_sync();
+    if (threadIdx.x < HD) {
+      // merge the warps in fixed order -> deterministic
+      const int d = threadIdx.x;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < MK_CW; ++w) M = fmaxf(M, wpart[w * 132 + 128]);
+      float Ls = 0.f, acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < MK_CW; ++w) {
+        const float mw = wpart[w * 132 + 128];
+        if (mw != -INFINITY) {
+          const float e = exp2f((mw - M) * LOG2E);
+          Ls = fmaf(wpart[w * 132 + 129], e, Ls);
+          acc = fmaf(wpart[w * 132 + d], e, acc);
         }
-        __syncwarp();
+      }
+      if (S == 1) {
+        p.attn[head * HD + d] = __float2bfloat16_rn(acc * (1.0f / Ls));
+      } else {
+        float* pp = p.part + ((size_t)head * p.nsplit + sp) * PART_STRIDE;
+        pp[d] = acc;
+        if (d == 0) { pp[128] = M; pp[129] = Ls; }
       }
     }
     cbar_sync();
-  }
-  if (cw < G) {
-    float* pp = p.part + ((size_t)head * p.nsplit + sp) * PART_STRIDE;
-    *reinterpret_cast<float4*>(pp + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    if (lane == 0) { pp[128] = m; pp[129] = l; }
   }
 }
 
@@ -551,8 +598,12 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
 // which removes the ticket + last-CTA merge + one more round trip from the critical path.
 __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p) {
   const int kv_len = p.st->pos + 1;
-  int chunk, nact;
-  mk_attn_geometry(p, kv_len, chunk, nact);
+  int nact, tps;
+  mk_attn_geometry(p, kv_len, nact, tps);
+  if (nact == 1) {                       // the attention CTAs already wrote the normalised heads
+    mk_stage_copy(xs, p.attn, p.n_heads * HD);
+    return;
+  }
   // (1) all (m, l) pairs in one parallel round trip -> shared memory (behind the activation vector)
   float* ml = reinterpret_cast<float*>(xs + p.n_heads * HD);            // [n_heads][nact][2]
   for (int i = threadIdx.x; i < p.n_heads * nact; i += MK_CTHREADS) {
@@ -650,10 +701,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   __syncthreads();
   if (warp >= MK_CW) {
     // ===== PRODUCERS / PREFETCHER: never wait for activations; run ahead across phases and layers =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MK_REGS_PRODUCER));
     if (warp < MK_CW + MK_PW) mk_producer(p, ring, lane, warp - MK_CW);
-    else mk_prefetcher(p, lane, consumed);
+    else if (warp == MK_CW + MK_PW) mk_prefetcher(p, lane, consumed);
     return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MK_REGS_CONSUMER));
 
   // ===== CONSUMERS =====
   const int cw = warp;
@@ -678,19 +731,45 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     cbar_sync();
   }
   const int pos = p.st->pos;
+  // per-step constants of the q/k/v epilogue: RoPE (cos, sin) per pair index and the page of `pos`
+  float* rope_cs = red + 64;                                   // [64][2]
+  if (threadIdx.x < HD / 2) {
+    float sn, cs;
+    sincosf(__fmul_rn((float)pos, p.inv_freq[threadIdx.x]), &sn, &cs);
+    rope_cs[2 * threadIdx.x] = cs; rope_cs[2 * threadIdx.x + 1] = sn;
+  }
+  const int page_pos = p.block_table[pos / PAGE];
+  // attention geometry is fixed for the whole step
+  int att_S, att_tps;
+  mk_attn_geometry(p, pos + 1, att_S, att_tps);
+  const int att_tile0 = ((int)blockIdx.x % att_S) * att_tps + cw;        // this warp's first tile (if the CTA has an attention task)
+  const bool att_has = (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
+  const int att_phys0 = att_has ? p.block_table[(att_tile0 << 5) / PAGE] : 0;
+  cbar_sync();
   const int tok_in = p.token_in != nullptr ? __ldcg(p.token_in) : p.st->token;
   const bf16* cur = p.embed != nullptr ? p.embed + (size_t)min(max(tok_in, 0), p.vocab - 1) * p.H : p.x_in;
 
-#define MK_STAMP(i) do { if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * 16 + (i)] = gtimer(); } while (0)
+#define MK_STAMP(i) do { if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * MK_DBG_WORDS + (i)] = gtimer(); } while (0)
   for (int li = 0; li < p.n_layers; ++li) {
     const MkLayer L = p.layers[li];
     bf16* nxt = (li == p.n_layers - 1) ? p.x_out : ((li & 1) ? p.xb : p.xa);
     MK_STAMP(0);
+    if (att_has && lane == 0) {
+      // pull this warp's K and V tile (8 KiB each, contiguous inside the page) toward L2 now; the
+      // loads after the next grid barrier then hit L2 instead of HBM
+      const int kvh0 = ((int)blockIdx.x / att_S) / G;
+      const int nt0 = min(32, pos + 1 - (att_tile0 << 5));
+      const bf16* kb = L.kv_pool + (((size_t)att_phys0 * 2) * p.n_kv + kvh0) * (PAGE * HD) + (size_t)((att_tile0 << 5) % PAGE) * HD;
+      const uint64_t polk = l2_policy_evict_last();
+      tma_prefetch_l2(kb, (uint32_t)nt0 * HD * 2u, polk);
+      tma_prefetch_l2(kb + (size_t)p.n_kv * (PAGE * HD), (uint32_t)nt0 * HD * 2u, polk);
+    }
 
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
     MK_STAMP(1);
-    mk_consume(p, PH_QKV, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_QKV, li, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+               [&](int vr, float v, bool owner, int) {
       const int task = vr >> 1, which = vr & 1;
       const int slot = task >> 6, d = task & 63;
       int kind = 0, hrow = slot;
@@ -704,17 +783,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       if (!owner) return;
       float o = y;
       if (kind != 2) {
-        const float theta = __fmul_rn((float)pos, p.inv_freq[d]);
-        float sn, cs;
-        sincosf(theta, &sn, &cs);
+        const float cs = rope_cs[2 * d], sn = rope_cs[2 * d + 1];     // per-step table (same sincosf(pos * inv_freq[d]))
         o = which == 0 ? __fsub_rn(__fmul_rn(y, cs), __fmul_rn(yp, sn)) : __fadd_rn(__fmul_rn(yp, sn), __fmul_rn(y, cs));
         o = bf16r(o);
       }
       if (kind == 0) {
         p.qbuf[hrow * HD + dim] = __float2bfloat16_rn(o);
       } else {
-        const int page = p.block_table[pos / PAGE];
-        const size_t off = (((size_t)page * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
+        const size_t off = (((size_t)page_pos * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
         L.kv_pool[off] = __float2bfloat16_rn(o);
       }
     });
@@ -723,7 +799,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     MK_STAMP(3);
 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
-    mk_attention<G>(p, L, scratch, cw, lane);
+    mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
     mk_grid_barrier(p, bar_base, bar_k);
     MK_STAMP(5);
@@ -731,10 +807,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P3: merge attention splits -> o_proj + residual
     mk_stage_attn_merge(xs, p);
     MK_STAMP(6);
-    mk_consume(p, PH_O, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_O, li, ring, xs, cw, lane, consumed, ncons,
+               [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr) : (unsigned short)0; },
+               [&](int vr, float v, bool owner, unsigned short xb_) {
       if (!owner) return;
+      if (!MK_OPT_PRE) xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
       const float o = bf16r(v);
-      const unsigned short xb_ = __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr);
       p.hbuf[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(xb_)), o));
     });
     MK_STAMP(7);
@@ -744,7 +822,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
     MK_STAMP(9);
-    mk_consume(p, PH_GU, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_GU, li, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+               [&](int vr, float v, bool owner, int) {
       const float y = bf16r(v);
       const float u = __shfl_xor_sync(0xffffffffu, y, 16);
       if (!owner || (vr & 1)) return;
@@ -759,10 +838,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
     MK_STAMP(12);
-    mk_consume(p, PH_DOWN, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_DOWN, li, ring, xs, cw, lane, consumed, ncons,
+               [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr) : (unsigned short)0; },
+               [&](int vr, float v, bool owner, unsigned short hb) {
       if (!owner) return;
+      if (!MK_OPT_PRE) hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
       const float o = bf16r(v);
-      const unsigned short hb = __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr);
       nxt[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(hb)), o));
     });
     MK_STAMP(13);
@@ -776,7 +857,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_stage_rmsnorm(xs, red, cur, p.norm_w, p.H, p.eps);
     float hm = -INFINITY, hl = 0.f;
     int hi = 0x7fffffff;
-    mk_consume(p, PH_HEAD, ring, xs, cw, lane, consumed, ncons, [&](int vr, float v, bool owner) {
+    mk_consume(p, PH_HEAD, 0, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+               [&](int vr, float v, bool owner, int) {
       if (!owner) return;
       const float lg = bf16r(v);
       p.logits_bf16[vr] = __float2bfloat16_rn(v);

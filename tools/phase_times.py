@@ -30,9 +30,10 @@ lib.dn_set_option(b"mk_debug", 1)
 pol._graph_step(ns, ns.x1, True, run, True)
 rt.compute_stream.synchronize()
 sms = lib.dn_device_sm_count()
-buf = (C.c_uint64 * (sms * L * 16))()
-n = lib.dn_step_debug(rt.model._h, buf, sms * L * 16, rt.compute_stream_ptr)
-a = np.frombuffer(buf, dtype=np.uint64).reshape(sms, L, 16).astype(np.int64)
+W = 32
+buf = (C.c_uint64 * (sms * L * W))()
+n = lib.dn_step_debug(rt.model._h, buf, sms * L * W, rt.compute_stream_ptr)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(sms, L, W).astype(np.int64)
 names = ["stage_norm1", "consume_qkv", "bar1", "attention", "bar2", "merge_stage", "consume_o", "bar3", "stage_norm2", "consume_gu", "bar4", "stage_act", "consume_down", "bar5"]
 d = np.diff(a[:, :, :15], axis=2)          # [sm][layer][14]
 mid = d[:, 4:28, :]
@@ -50,3 +51,7 @@ print("consume_gu per CTA (mean over layers): fastest", [(int(i), int(per[i])) f
 print("std over layers within a CTA (mean)", gu.std(axis=1).mean(), " std across CTAs of the per-CTA mean", per.std())
 dn = d[:, 4:28, 12].mean(axis=1)
 print("corr(consume_gu, consume_down) across CTAs", float(np.corrcoef(per, dn)[0, 1]))
+
+pb = a[:, 4:28, 16:20]; cwt = a[:, 4:28, 24:28]
+print("producer-0 blocked on a full ring, ns per layer while producing [qkv, o, gu, down] (mean over SMs):", pb.mean(axis=(0, 1)).round(0).tolist(), "sum", float(pb.sum(axis=2).mean()))
+print("consumer warp 0 waiting for weights (ring empty), ns per layer in [qkv, o, gu, down]:", cwt.mean(axis=(0, 1)).round(0).tolist(), "sum", float(cwt.sum(axis=2).mean()))
