@@ -40,6 +40,7 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
+static int g_inflight = 3;      // step kernel: cap on ring stages with loads outstanding (0 = no cap); measured 2/3/4/5/none = 357/381/374/369/366 tok/s
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
 static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
@@ -245,6 +246,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
+  if (!strcmp(key, "inflight")) { g_inflight = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "attn_chunk")) { g_attn_chunk = value < 32 ? 32 : (int)((value + 31) / 32 * 32); return DN_OK; }
   if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
   if (!strcmp(key, "pf_depth")) { g_pf_depth = value < 0 ? 0 : (int)value; return DN_OK; }
@@ -804,6 +806,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
   p.attn_chunk = g_attn_chunk;
+  p.inflight = g_inflight;
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
   p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;
@@ -827,7 +830,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   if (scratch < merge_bytes) scratch = merge_bytes;
   if (c.hidden > 8192) return fail(DN_EINVAL, "hidden > 8192 unsupported by the step kernel's RMSNorm staging");
   scratch = (scratch + 1023) / 1024 * 1024;
-  const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4 + 128 * 4;   // barriers, misc scratch, RoPE table
+  const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4 + 128 * 4 + 2 * 8 * 16 * 4;   // barriers, misc scratch, RoPE table, row-block partials
   int stages = (227 * 1024 - scratch - tail) / MK_STAGE_BYTES;
   if (stages > MK_MAX_STAGES) stages = MK_MAX_STAGES;
   if (stages < 2) return fail(DN_EINVAL, "model too wide for the megakernel's shared-memory ring");

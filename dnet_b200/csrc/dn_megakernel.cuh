@@ -33,7 +33,10 @@ constexpr int MK_THREADS = MK_CTHREADS + 4 * 32;   // + one warpgroup: 2 produce
 constexpr int MK_REGS_CONSUMER = 224, MK_REGS_PRODUCER = 56;
 constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
 constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
-constexpr int MK_STAGE_BYTES = MK_ROWS * MK_MAX_SEG * 2;   // 32 KB
+// rows sit 16 bytes further apart than their payload, so the 8 row addresses of an ldmatrix fall
+// into 8 different bank groups (a 2 KiB pitch would put them all on the same 4 banks)
+constexpr int MK_ROW_PITCH = MK_MAX_SEG * 2 + 16;   // 2064
+constexpr int MK_STAGE_BYTES = MK_ROWS * MK_ROW_PITCH;   // 33024
 constexpr int MK_MAX_STAGES = 8;
 // r01 measurement: with 512-byte bulk copies the step ran at 2.2 TB/s (one TMA op per ~66
 // cycles per SM is the limit, not bytes), so a stage is 16 rows x 1024 columns = 16 ops of 2 KiB.
@@ -82,6 +85,7 @@ struct MkParams {
   const uint32_t* wait_flag; uint32_t wait_seq;
   const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
   void* send_dst; uint32_t* send_flag; uint32_t send_seq;
+  int inflight;              // producer: at most this many ring stages with loads outstanding (0 = whole ring)
   int attn_chunk;            // minimum tokens per attention split (multiple of 32)
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
@@ -178,6 +182,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
 // passed when the counter reaches base + (k+1)*grid, where base is the counter value at launch
 // start (published by the previous launch in bar_epoch) -- one atomic round trip + one poll.
 __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int base, unsigned int& k) {
+  if (p.flags & 8) {     // flags bit3: timing experiment (streaming ceiling): no grid-wide wait; the count still advances
+    cbar_sync();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
+    ++k;
+    return;
+  }
   cbar_sync();
   if ((p.flags & 1) && threadIdx.x == 0) {
     // two-word variant: the last arriver resets the count and bumps a generation word
@@ -297,11 +307,17 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
     const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
     for (int sg = 0; sg < nseg; ++sg) {
       if ((int)(idx % MK_PW) == which) {
+        if (p.inflight > 0 && idx >= (unsigned)p.inflight) {
+          // bound the bytes in flight (not the buffered bytes): a deep queue of outstanding bulk loads
+          // is what the grid barrier's polls and every staging load have to wait behind
+          const unsigned int j = idx - (unsigned)p.inflight;
+          mbar_wait(&ring.full[j % (unsigned)ring.n_stages], (j / (unsigned)ring.n_stages) & 1u, p.err);
+        }
         mbar_wait_dbg(&ring.empty[ring.stage], ring.phase ^ 1u, p.err, accp);
         if (lane == 0) mbar_arrive_expect_tx(&ring.full[ring.stage], (uint32_t)nv * rowbytes);
         __syncwarp();
         if (lane < nv)
-          tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * rowbytes,
+          tma_bulk_g2s(ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)lane * MK_ROW_PITCH,
                        src + (size_t)sg * d.seg, rowbytes, &ring.full[ring.stage], pol);
       }
       ++idx;
@@ -376,44 +392,66 @@ __device__ __forceinline__ void mk_prefetcher(const MkParams& p, int lane, volat
 }
 
 // ---------------------------------------------------------------------------------
-// consumer: one GEMV phase.  Epi is called by every lane with (vr, v, partner, valid); the
-// lanes 0 and 16 are the row owners (2 rows per warp per block); the partner row of a
-// RoPE / SwiGLU pair sits 16 lanes away.
+// consumer: one GEMV phase on the tensor cores.  A ring stage holds 16 weight rows x seg columns;
+// consumer warp w owns the column slice [w*seg/8, (w+1)*seg/8) of all 16 rows and feeds it to
+// mma.m16n8k16 (A = weights via ldmatrix, B = the activation slice replicated over the 8 n columns,
+// fp32 accumulators).  The bf16 x bf16 products are exact and accumulate in fp32, as in the scalar
+// formulation; per stage a warp issues 8 ldmatrix + 16 LDS.32 + 8 mma instead of ~170 ALU ops,
+// which is what lets the phase run at the HBM rate (the scalar loop was the bottleneck: the ring
+// stayed full).  At the end of a 16-row block the 8 per-warp partial sums of each row are added in
+// fixed warp order (deterministic) by the block's epilogue warp (rotating), whose lanes 0..15 own
+// rows rb+lane; the RoPE / SwiGLU partner row sits in the adjacent lane.
+//   pre(vr, owner)  -> value   issued before the block's stages (hides the epilogue's global load)
+//   epi(vr, v, owner, value)   called by all 32 lanes of the epilogue warp
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 template <class Pre, class Epi>
-__device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, MkRing& ring, const bf16* xs, int cw, int lane,
-                                           volatile unsigned int* consumed, unsigned int& ncons, Pre pre, Epi epi) {
+__device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, MkRing& ring, const bf16* xs, float* red2, int cw, int lane,
+                                           volatile unsigned int* consumed, unsigned int& ncons, unsigned int& nblk, Pre pre, Epi epi) {
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(p, ph, d, r0, r1);
   const int nseg = d.K / d.seg;
-  const int nch = d.seg >> 8;
-  const int rowbytes = d.seg * 2;
+  const int slice = d.seg >> 3;                 // columns per warp per stage: 128 / 64 / 32
+  const int ksteps = slice >> 4;
   unsigned long long waited = 0;
   unsigned long long* accp = (p.dbg != nullptr && cw == 0) ? &waited : nullptr;
+  // ldmatrix: lane l addresses row (l&7) + 8*((l>>3)&1) of the 16, 16-byte chunk (l>>4) of the k16 step
+  const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * MK_ROW_PITCH + (lane >> 4) * 16 + cw * slice * 2);
+  const uint32_t ring_base = smem_u32(ring.data);
+  const int t = lane & 3, g = lane >> 2;
   for (int rb = r0; rb < r1; rb += MK_ROWS) {
     const int nv = min(MK_ROWS, r1 - rb);
-    const int myrows = min(2, max(0, nv - 2 * cw));
-    // row-owner lanes issue their epilogue's global loads now, so the round trip hides under the block's stages
-    const int r_own = 2 * cw + ((lane >> 4) & 1);
-    const bool owner_lane = r_own < nv && (lane & 15) == 0;
-    const auto pv = pre(rb + r_own, owner_lane);
-    float acc[2] = {0.f, 0.f};
+    const int ew = (int)(nblk & (MK_CW - 1)), buf = (int)(nblk & 1u);
+    const bool owner = (cw == ew) && lane < nv;
+    const auto pv = pre(rb + lane, owner);
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
     for (int sg = 0; sg < nseg; ++sg) {
       mbar_wait_dbg(&ring.full[ring.stage], ring.phase, p.err, accp);
-      if (myrows > 0 && !(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
-        const unsigned char* tile = ring.data + (size_t)ring.stage * MK_STAGE_BYTES + (size_t)(2 * cw) * rowbytes + lane * 16;
-        const bf16* xseg = xs + (size_t)sg * d.seg + (lane << 3);
-#pragma unroll 4
-        for (int ch = 0; ch < nch; ++ch) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(xseg + (ch << 8));
-          const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
-                               bf_lo(xv.z), bf_hi(xv.z), bf_lo(xv.w), bf_hi(xv.w)};
-          const uint4 w0 = *reinterpret_cast<const uint4*>(tile + (ch << 9));
-          acc[0] = dot8(w0, xf, acc[0]);
-          if (myrows > 1) {
-            const uint4 w1 = *reinterpret_cast<const uint4*>(tile + rowbytes + (ch << 9));
-            acc[1] = dot8(w1, xf, acc[1]);
+      if (!(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
+        const uint32_t a_base = ring_base + (uint32_t)ring.stage * MK_STAGE_BYTES + a_lane;
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs + (size_t)sg * d.seg + cw * slice) + t;
+        if (ksteps == 8) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            uint32_t a0, a1, a2, a3, e0, e1, e2, e3;
+            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+            ldmatrix_x4(a_base + j * 32 + 32, e0, e1, e2, e3);
+            mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+            mma_bf16_16816(c1, e0, e1, e2, e3, xw[j * 8 + 8], xw[j * 8 + 12]);
+          }
+        } else {
+          for (int j = 0; j < ksteps; ++j) {
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+            mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
           }
         }
       }
@@ -423,15 +461,23 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, Mk
       if (threadIdx.x == 0) *consumed = ncons;      // progress signal for the L2 prefetch warp
       ring.advance();
     }
-    // 2 values per lane -> lanes 0-15 end with row 2*cw, lanes 16-31 with row 2*cw + 1
-    const bool up = (lane & 16) != 0;
-    const float keep = up ? acc[1] : acc[0], send = up ? acc[0] : acc[1];
-    float v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    epi(rb + r_own, v, owner_lane, pv);
+    // every column of the accumulator tile holds the same dot product: lanes with t == 0 publish
+    // rows g (c[0]) and g + 8 (c[2]) of this warp's column slice
+    if (t == 0) {
+      float* r = red2 + (buf * MK_CW + cw) * MK_ROWS;
+      r[g] = c0[0] + c1[0];
+      r[g + 8] = c0[2] + c1[2];
+    }
+    cbar_sync();
+    if (cw == ew) {
+      float v = 0.f;
+      if (lane < MK_ROWS) {
+#pragma unroll
+        for (int w = 0; w < MK_CW; ++w) v += red2[(buf * MK_CW + w) * MK_ROWS + lane];
+      }
+      epi(rb + lane, v, owner, pv);
+    }
+    ++nblk;
   }
   // mk_debug: ns consumer warp 0 waited for weights (ring empty = HBM-bound time) in this phase
   if (accp != nullptr && lane == 0 && ph < 4) p.dbg[((size_t)blockIdx.x * p.n_layers + li) * MK_DBG_WORDS + 24 + ph] = waited;
@@ -711,7 +757,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   // ===== CONSUMERS =====
   const int cw = warp;
   bf16* xs = reinterpret_cast<bf16*>(scratch);
-  unsigned int bar_k = 0, ncons = 0;
+  unsigned int bar_k = 0, ncons = 0, nblk = 0;
+  float* red2 = red + 192;                                     // [2][MK_CW][MK_ROWS] row-block partial sums
   const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
   if (p.wait_flag != nullptr) {
     // the weights of this step are already streaming into the ring while we wait for the hop
@@ -768,7 +815,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
     MK_STAMP(1);
-    mk_consume(p, PH_QKV, li, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+    mk_consume(p, PH_QKV, li, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       const int task = vr >> 1, which = vr & 1;
       const int slot = task >> 6, d = task & 63;
@@ -779,7 +826,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       const bf16* bias = L.w[kind == 0 ? MK_W_QB : (kind == 1 ? MK_W_KB : MK_W_VB)];
       if (owner && bias != nullptr) v += __bfloat162float(bias[hrow * HD + dim]);
       const float y = bf16r(v);
-      const float yp = __shfl_xor_sync(0xffffffffu, y, 16);
+      const float yp = __shfl_xor_sync(0xffffffffu, y, 1);
       if (!owner) return;
       float o = y;
       if (kind != 2) {
@@ -807,7 +854,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P3: merge attention splits -> o_proj + residual
     mk_stage_attn_merge(xs, p);
     MK_STAMP(6);
-    mk_consume(p, PH_O, li, ring, xs, cw, lane, consumed, ncons,
+    mk_consume(p, PH_O, li, ring, xs, red2, cw, lane, consumed, ncons, nblk,
                [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr) : (unsigned short)0; },
                [&](int vr, float v, bool owner, unsigned short xb_) {
       if (!owner) return;
@@ -822,10 +869,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
     MK_STAMP(9);
-    mk_consume(p, PH_GU, li, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+    mk_consume(p, PH_GU, li, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       const float y = bf16r(v);
-      const float u = __shfl_xor_sync(0xffffffffu, y, 16);
+      const float u = __shfl_xor_sync(0xffffffffu, y, 1);
       if (!owner || (vr & 1)) return;
       const float s = bf16r(1.0f / (1.0f + expf(-y)));
       const float a = bf16r(__fmul_rn(y, s));
@@ -838,7 +885,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
     MK_STAMP(12);
-    mk_consume(p, PH_DOWN, li, ring, xs, cw, lane, consumed, ncons,
+    mk_consume(p, PH_DOWN, li, ring, xs, red2, cw, lane, consumed, ncons, nblk,
                [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr) : (unsigned short)0; },
                [&](int vr, float v, bool owner, unsigned short hb) {
       if (!owner) return;
@@ -857,7 +904,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_stage_rmsnorm(xs, red, cur, p.norm_w, p.H, p.eps);
     float hm = -INFINITY, hl = 0.f;
     int hi = 0x7fffffff;
-    mk_consume(p, PH_HEAD, 0, ring, xs, cw, lane, consumed, ncons, [&](int, bool) { return 0; },
+    mk_consume(p, PH_HEAD, 0, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       if (!owner) return;
       const float lg = bf16r(v);

@@ -15,6 +15,7 @@ cfg = dict(B.LLAMA3_8B); L = cfg["num_hidden_layers"]
 rt = ShardRuntime(0); rt.kv_cache_config.max_tokens = 512
 rt.load_model_core(ShardLoadModelRequest(model_path=SyntheticSource(cfg, 0), total_layers=L, layers=list(range(L)), window_size=L, residency_size=L, kv_bits="fp16"))
 lib.dn_set_option(b"pf_depth", int(os.environ.get("PF", "0")))
+lib.dn_set_option(b"inflight", int(os.environ.get("INFLIGHT", "0")))
 pol = rt.policy
 g = torch.Generator().manual_seed(1234)
 prompt = torch.randint(0, cfg["vocab_size"], (128,), generator=g).tolist()
