@@ -40,6 +40,7 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
+static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
 static int g_inflight = 3;      // step kernel: cap on ring stages with loads outstanding (0 = no cap); measured 2/3/4/5/none = 357/381/374/369/366 tok/s
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
 static int g_mk_debug = 0;
@@ -246,6 +247,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
+  if (!strcmp(key, "park")) { g_park = value != 0; return DN_OK; }
   if (!strcmp(key, "inflight")) { g_inflight = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "attn_chunk")) { g_attn_chunk = value < 32 ? 32 : (int)((value + 31) / 32 * 32); return DN_OK; }
   if (!strcmp(key, "mk_flags")) { g_mk_flags = (int)value; return DN_OK; }
@@ -807,6 +809,8 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.pf_depth = g_pf_depth;
   p.attn_chunk = g_attn_chunk;
   p.inflight = g_inflight;
+  // TMEM parking needs one fragment geometry (seg == 1024) in every phase
+  p.park = (g_park && c.hidden % 1024 == 0 && c.ffn % 1024 == 0 && (c.n_heads * HD) % 1024 == 0) ? 1 : 0;
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
   p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;

@@ -29,8 +29,10 @@ constexpr int MK_CTHREADS = MK_CW * 32;         // 256
 constexpr int MK_PW = 2;                        // producer warps (alternate ring stages)
 constexpr int MK_THREADS = MK_CTHREADS + 4 * 32;   // + one warpgroup: 2 producers, the L2 prefetch warp, 1 idle warp
 // register re-allocation (setmaxnreg works per warpgroup): the data-movement warpgroup gives most
-// of its registers to the 8 consumer warps.  8*32*224 + 4*32*56 = 64512 <= 65536
+// of its registers to the 8 consumer warps.  8*32*224 + 4*32*56 = 64512 = 168*384
 constexpr int MK_REGS_CONSUMER = 224, MK_REGS_PRODUCER = 56;
+// the pool is what the CTA got at launch (168 regs x 384 threads), NOT the whole file: asking for more blocks forever
+static_assert(8 * 32 * MK_REGS_CONSUMER + 4 * 32 * MK_REGS_PRODUCER <= 168 * MK_THREADS, "setmaxnreg split exceeds the CTA's launch allocation");
 constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
 constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
 // rows sit 16 bytes further apart than their payload, so the 8 row addresses of an ldmatrix fall
@@ -85,6 +87,7 @@ struct MkParams {
   const uint32_t* wait_flag; uint32_t wait_seq;
   const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
   void* send_dst; uint32_t* send_flag; uint32_t send_seq;
+  int park;                  // 1: consumer warps park ready ring stages in tensor memory while they wait at a grid barrier
   int inflight;              // producer: at most this many ring stages with loads outstanding (0 = whole ring)
   int attn_chunk;            // minimum tokens per attention split (multiple of 32)
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
@@ -146,6 +149,51 @@ __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, un
   mbar_wait(bar, parity, err);
   *acc_ns += gtimer() - t0;
 }
+
+// ---------------------------------------------------------------------------------
+// tensor memory as a second-level weight buffer.  While the consumers sit in a grid barrier the
+// ring would fill up and HBM would go idle; instead every consumer warp keeps draining ready
+// stages: it runs the same 8 ldmatrix it would run to consume its column slice of the stage and
+// parks the 32 fragment registers in its own TMEM region (lanes of its quarter, 32 columns per
+// stage, 8 stages per warp = all 256 KiB), then frees the ring slot.  After the barrier the warp
+// reads the fragments back (tcgen05.ld) in the same order and feeds them to the same mma sequence,
+// so results do not depend on where a stage waited.
+// ---------------------------------------------------------------------------------
+constexpr int MK_PARK_SLOTS = 8;
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {     // never suspends
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void st_release_cta(unsigned int* sp, unsigned int v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sp)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_cta(const unsigned int* sp) {
+  unsigned int v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sp)) : "memory");
+  return v;
+}
 // L2 eviction policies: weights are read exactly once per step, so demand loads are marked
 // evict-first (they must not push KV pages, activations or prefetched tiles out of L2) and
 // look-ahead prefetches evict-last (they must survive until the ring asks for them)
@@ -175,56 +223,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-
-// grid barrier among the consumer warps of all CTAs (all CTAs are co-resident: grid = #SMs,
-// one CTA per SM, launched cooperatively).  One monotonic counter: barrier k of this launch is
-// passed when the counter reaches base + (k+1)*grid, where base is the counter value at launch
-// start (published by the previous launch in bar_epoch) -- one atomic round trip + one poll.
-__device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int base, unsigned int& k) {
-  if (p.flags & 8) {     // flags bit3: timing experiment (streaming ceiling): no grid-wide wait; the count still advances
-    cbar_sync();
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
-    ++k;
-    return;
-  }
-  cbar_sync();
-  if ((p.flags & 1) && threadIdx.x == 0) {
-    // two-word variant: the last arriver resets the count and bumps a generation word
-    const unsigned int gen = ld_acquire_gpu(p.bar_gen);
-    __threadfence();
-    const unsigned int arrived = atomicAdd(p.bar_count, 1u);
-    if (arrived == gridDim.x - 1) {
-      atomicExch(p.bar_count, 0u);
-      __threadfence();
-      atomicAdd(p.bar_gen, 1u);
-    } else {
-      const unsigned long long t0 = gtimer();
-      unsigned it = 0;
-      while (ld_acquire_gpu(p.bar_gen) == gen) {
-        if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
-      }
-    }
-    __threadfence();
-  } else if (threadIdx.x == 0) {
-    // release-arrive / acquire-poll: the CTA barrier above orders every consumer thread's writes
-    // before this release (cumulativity), the one below orders their reads after the acquire.
-    // Cross-CTA activations are read with ld.global.cg (L2), so no L1 invalidation is needed.
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
-    const unsigned int target = base + (k + 1u) * gridDim.x;
-    if ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
-      const unsigned long long t0 = gtimer();
-      unsigned it = 0;
-      while ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
-        if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) {
-          atomicExch(p.err, 3u);
-          break;
-        }
-      }
-    }
-  }
-  k += 1u;
-  cbar_sync();
 }
 
 // ---------------------------------------------------------------------------------
@@ -412,9 +410,87 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// per-warp consumer position: stages [cons_n, ring_n) of this warp's column slice are parked in TMEM
+struct MkCons {
+  uint32_t tmem;          // this warp's TMEM region (lane quarter | column half)
+  bool park;              // parking needs seg == 1024 in every phase (one fragment geometry)
+  unsigned int cons_n;    // stages consumed so far
+  unsigned int ring_n;    // stages taken out of the shared-memory ring (consumed or parked)
+  uint32_t a_lane;        // ldmatrix lane offset at seg == 1024
+};
+__device__ __forceinline__ bool mk_try_park(MkRing& ring, MkCons& cs, int lane) {
+  if (cs.ring_n - cs.cons_n >= (unsigned)MK_PARK_SLOTS) return false;
+  if (!mbar_test_wait(&ring.full[ring.stage], ring.phase)) return false;
+  uint32_t r[32];
+  const uint32_t a_base = smem_u32(ring.data) + (uint32_t)ring.stage * MK_STAGE_BYTES + cs.a_lane;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ldmatrix_x4(a_base + j * 32, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  tmem_st32(cs.tmem + (cs.ring_n % MK_PARK_SLOTS) * 32u, r);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
+  ring.advance();
+  ++cs.ring_n;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------
+// grid-wide barrier between dependent phases.  All CTAs are co-resident (cooperative launch,
+// grid == #SMs).  The arrival counter only ever grows: barrier k of this launch is passed when it
+// reaches base + (k+1)*grid, base being the value the previous launch published in bar_epoch.
+// Consumer thread 0 release-arrives and posts a request to the poller warp, which acquire-polls
+// the counter and publishes completion in shared memory; the 8 consumer warps meanwhile park ready
+// ring stages in TMEM, so the weight stream keeps flowing through the wait.
+// Cross-CTA activations are read with ld.global.cg (L2), so no L1 invalidation is needed.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int& k, MkRing& ring, MkCons& cs, unsigned int* bar_req,
+                                                unsigned int* bar_done, int lane) {
+  cbar_sync();          // every consumer thread's writes precede thread 0's release (cumulativity)
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
+    if (!(p.flags & 8)) st_release_cta(bar_req, k + 1u);
+  }
+  ++k;
+  if (p.flags & 8) return;     // flags bit3: timing experiment (streaming ceiling): no grid-wide wait
+  const unsigned long long t0 = gtimer();
+  unsigned it = 0;
+  for (;;) {
+    unsigned int done = 0;
+    if (lane == 0) done = ld_acquire_cta(bar_done);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done == k) break;
+    const bool parked = cs.park && mk_try_park(ring, cs, lane);
+    if (!parked && (++it & 1023u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
+  }
+  __syncwarp();
+}
+// the poller warp (one lane): serves the consumers' barrier requests until told to exit
+__device__ __forceinline__ void mk_barrier_poller(const MkParams& p, unsigned int* bar_req, unsigned int* bar_done) {
+  unsigned int served = 0;
+  for (;;) {
+    unsigned int req;
+    const unsigned long long t0 = gtimer();
+    unsigned it = 0;
+    while ((req = ld_acquire_cta(bar_req)) == served) {
+      __nanosleep(32);
+      if ((++it & 4095u) == 0 && gtimer() - t0 > 8ull * MK_TIMEOUT_NS) return;
+    }
+    if (req == 0xffffffffu) return;
+    const unsigned int target = bar_req[2] + req * gridDim.x;      // launch base, stored by consumer thread 0 before its first request
+    if ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
+      const unsigned long long t1 = gtimer();
+      unsigned it2 = 0;
+      while ((int)(ld_acquire_gpu(p.bar_count) - target) < 0) {
+        if ((++it2 & 255u) == 0 && gtimer() - t1 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
+      }
+    }
+    st_release_cta(bar_done, req);
+    served = req;
+  }
+}
+
 template <class Pre, class Epi>
 __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, MkRing& ring, const bf16* xs, float* red2, int cw, int lane,
-                                           volatile unsigned int* consumed, unsigned int& ncons, unsigned int& nblk, Pre pre, Epi epi) {
+                                           volatile unsigned int* consumed, MkCons& cs, unsigned int& nblk, Pre pre, Epi epi) {
   const MkPhase d = mk_phase(p, ph);
   int r0, r1;
   mk_range(p, ph, d, r0, r1);
@@ -434,32 +510,46 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, Mk
     const auto pv = pre(rb + lane, owner);
     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
     for (int sg = 0; sg < nseg; ++sg) {
-      mbar_wait_dbg(&ring.full[ring.stage], ring.phase, p.err, accp);
-      if (!(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
-        const uint32_t a_base = ring_base + (uint32_t)ring.stage * MK_STAGE_BYTES + a_lane;
-        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs + (size_t)sg * d.seg + cw * slice) + t;
-        if (ksteps == 8) {
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs + (size_t)sg * d.seg + cw * slice) + t;
+      if (cs.cons_n != cs.ring_n) {
+        // this stage was parked in TMEM during a barrier: same fragments, same mma order
+        uint32_t r[32];
+        tmem_ld32(cs.tmem + (cs.cons_n % MK_PARK_SLOTS) * 32u, r);
+        if (!(p.flags & 4)) {
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            uint32_t a0, a1, a2, a3, e0, e1, e2, e3;
-            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
-            ldmatrix_x4(a_base + j * 32 + 32, e0, e1, e2, e3);
-            mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
-            mma_bf16_16816(c1, e0, e1, e2, e3, xw[j * 8 + 8], xw[j * 8 + 12]);
-          }
-        } else {
-          for (int j = 0; j < ksteps; ++j) {
-            uint32_t a0, a1, a2, a3;
-            ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
-            mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+            mma_bf16_16816(c0, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3], xw[j * 8], xw[j * 8 + 4]);
+            mma_bf16_16816(c1, r[4 * j + 4], r[4 * j + 5], r[4 * j + 6], r[4 * j + 7], xw[j * 8 + 8], xw[j * 8 + 12]);
           }
         }
+      } else {
+        mbar_wait_dbg(&ring.full[ring.stage], ring.phase, p.err, accp);
+        if (!(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
+          const uint32_t a_base = ring_base + (uint32_t)ring.stage * MK_STAGE_BYTES + a_lane;
+          if (ksteps == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              uint32_t a0, a1, a2, a3, e0, e1, e2, e3;
+              ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+              ldmatrix_x4(a_base + j * 32 + 32, e0, e1, e2, e3);
+              mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+              mma_bf16_16816(c1, e0, e1, e2, e3, xw[j * 8 + 8], xw[j * 8 + 12]);
+            }
+          } else {
+            for (int j = 0; j < ksteps; ++j) {
+              uint32_t a0, a1, a2, a3;
+              ldmatrix_x4(a_base + j * 32, a0, a1, a2, a3);
+              mma_bf16_16816(c0, a0, a1, a2, a3, xw[j * 8], xw[j * 8 + 4]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
+        ring.advance();
+        ++cs.ring_n;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
-      ++ncons;
-      if (threadIdx.x == 0) *consumed = ncons;      // progress signal for the L2 prefetch warp
-      ring.advance();
+      ++cs.cons_n;
+      if (threadIdx.x == 0) *consumed = cs.cons_n;      // progress signal for the L2 prefetch warp
     }
     // every column of the accumulator tile holds the same dot product: lanes with t == 0 publish
     // rows g (c[0]) and g + 8 (c[2]) of this warp's column slice
@@ -743,13 +833,24 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   __syncthreads();
 
   volatile unsigned int* consumed = reinterpret_cast<volatile unsigned int*>(red + 48);
-  if (threadIdx.x == 0) *consumed = 0u;
+  unsigned int* tmem_slot = reinterpret_cast<unsigned int*>(red + 56);
+  unsigned int* bar_req = reinterpret_cast<unsigned int*>(red + 57);
+  unsigned int* bar_done = reinterpret_cast<unsigned int*>(red + 58);
+  if (threadIdx.x == 0) { *consumed = 0u; *bar_req = 0u; *bar_done = 0u; *tmem_slot = 0u; }
+  if (p.park && warp == 0) {
+    // all 512 TMEM columns: 8 consumer warps x 8 parked stages x 32 columns (one CTA per SM, so nothing else wants them)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp >= MK_CW) {
-    // ===== PRODUCERS / PREFETCHER: never wait for activations; run ahead across phases and layers =====
+    // ===== PRODUCERS / PREFETCHER / BARRIER POLLER: never wait for activations =====
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MK_REGS_PRODUCER));
     if (warp < MK_CW + MK_PW) mk_producer(p, ring, lane, warp - MK_CW);
     else if (warp == MK_CW + MK_PW) mk_prefetcher(p, lane, consumed);
+    else if (lane == 0) mk_barrier_poller(p, bar_req, bar_done);
     return;
   }
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MK_REGS_CONSUMER));
@@ -757,9 +858,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   // ===== CONSUMERS =====
   const int cw = warp;
   bf16* xs = reinterpret_cast<bf16*>(scratch);
-  unsigned int bar_k = 0, ncons = 0, nblk = 0;
+  unsigned int bar_k = 0, nblk = 0;
+  MkCons cs;
+  cs.park = p.park != 0;
+  cs.tmem = *reinterpret_cast<volatile unsigned int*>(tmem_slot) + ((uint32_t)(32 * (cw & 3)) << 16) + (uint32_t)((cw >> 2) * 256);
+  cs.cons_n = 0; cs.ring_n = 0;
+  cs.a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * MK_ROW_PITCH + (lane >> 4) * 16 + cw * 256);
   float* red2 = red + 192;                                     // [2][MK_CW][MK_ROWS] row-block partial sums
   const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
+  if (threadIdx.x == 0) bar_req[2] = bar_base;                 // red[59]: read by the poller after its first acquire of bar_req
   if (p.wait_flag != nullptr) {
     // the weights of this step are already streaming into the ring while we wait for the hop
     if (threadIdx.x == 0) {
@@ -815,7 +922,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
     MK_STAMP(1);
-    mk_consume(p, PH_QKV, li, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
+    mk_consume(p, PH_QKV, li, ring, xs, red2, cw, lane, consumed, cs, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       const int task = vr >> 1, which = vr & 1;
       const int slot = task >> 6, d = task & 63;
@@ -842,19 +949,19 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       }
     });
     MK_STAMP(2);
-    mk_grid_barrier(p, bar_base, bar_k);
+    mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(3);
 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
     mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
-    mk_grid_barrier(p, bar_base, bar_k);
+    mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(5);
 
     // ---- P3: merge attention splits -> o_proj + residual
     mk_stage_attn_merge(xs, p);
     MK_STAMP(6);
-    mk_consume(p, PH_O, li, ring, xs, red2, cw, lane, consumed, ncons, nblk,
+    mk_consume(p, PH_O, li, ring, xs, red2, cw, lane, consumed, cs, nblk,
                [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr) : (unsigned short)0; },
                [&](int vr, float v, bool owner, unsigned short xb_) {
       if (!owner) return;
@@ -863,13 +970,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       p.hbuf[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(xb_)), o));
     });
     MK_STAMP(7);
-    mk_grid_barrier(p, bar_base, bar_k);
+    mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(8);
 
     // ---- P4: RMSNorm -> gate/up -> SwiGLU
     mk_stage_rmsnorm(xs, red, p.hbuf, L.w[MK_W_LN2], p.H, p.eps);
     MK_STAMP(9);
-    mk_consume(p, PH_GU, li, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
+    mk_consume(p, PH_GU, li, ring, xs, red2, cw, lane, consumed, cs, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       const float y = bf16r(v);
       const float u = __shfl_xor_sync(0xffffffffu, y, 1);
@@ -879,13 +986,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       p.act[vr >> 1] = __float2bfloat16_rn(__fmul_rn(a, u));
     });
     MK_STAMP(10);
-    mk_grid_barrier(p, bar_base, bar_k);
+    mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(11);
 
     // ---- P5: down_proj + residual (+ cast to wire dtype == bf16 store)
     mk_stage_copy(xs, p.act, p.FFN);
     MK_STAMP(12);
-    mk_consume(p, PH_DOWN, li, ring, xs, red2, cw, lane, consumed, ncons, nblk,
+    mk_consume(p, PH_DOWN, li, ring, xs, red2, cw, lane, consumed, cs, nblk,
                [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(p.hbuf) + vr) : (unsigned short)0; },
                [&](int vr, float v, bool owner, unsigned short hb) {
       if (!owner) return;
@@ -894,7 +1001,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       nxt[vr] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(__ushort_as_bfloat16(hb)), o));
     });
     MK_STAMP(13);
-    mk_grid_barrier(p, bar_base, bar_k);
+    mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(14);
     cur = nxt;
   }
@@ -904,7 +1011,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     mk_stage_rmsnorm(xs, red, cur, p.norm_w, p.H, p.eps);
     float hm = -INFINITY, hl = 0.f;
     int hi = 0x7fffffff;
-    mk_consume(p, PH_HEAD, 0, ring, xs, red2, cw, lane, consumed, ncons, nblk, [&](int, bool) { return 0; },
+    mk_consume(p, PH_HEAD, 0, ring, xs, red2, cw, lane, consumed, cs, nblk, [&](int, bool) { return 0; },
                [&](int vr, float v, bool owner, int) {
       if (!owner) return;
       const float lg = bf16r(v);
@@ -981,7 +1088,17 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (p.advance) p.st->pos = pos + 1;
-    if (!(p.flags & 1)) *p.bar_epoch = bar_base + bar_k * gridDim.x;   // every CTA passed bar_k barriers; next launch starts here
+    *p.bar_epoch = bar_base + bar_k * gridDim.x;   // every CTA passed bar_k barriers; next launch starts here
+  }
+  if (threadIdx.x == 0) st_release_cta(bar_req, 0xffffffffu);          // poller warp: exit
+  if (p.park) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cbar_sync();                                                         // every warp is done with its TMEM region
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) {
+      const unsigned int tbase = *reinterpret_cast<volatile unsigned int*>(tmem_slot);
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+    }
   }
 }
 
