@@ -279,7 +279,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         from dnet_b200.shard.calibrate import calibrate
         tcal = time.perf_counter()
         calibrate(rt)
-        log(f"step-kernel partition calibrated in {time.perf_counter() - tcal:.2f}s")
+        log(f"step-kernel partition calibrated in {time.perf_counter() - tcal:.2f}s: {getattr(rt, 'calibration', None)}")
     log(f"model ready + prefill in {time.perf_counter() - t0:.1f}s; first token {first.token_id} lp {first.logprob}")
     run = list(range(L))
     stream = rt.compute_stream

@@ -1,11 +1,13 @@
 """Per-SM calibration of the step kernel's row partition.
 
-Measured on B200 (profiles/r01_step_phase_times.txt): with an equal split every SM streams the same
-bytes, yet the time an SM needs for its share differs persistently by up to +-8% between SMs
-(position relative to the two dies / HBM stacks), and every grid barrier waits for the slowest.
-``calibrate`` runs a few decode steps with the kernel's phase stamps on, converts each SM's
-consume time per phase into a speed, and re-partitions the rows proportionally (damped, 3 rounds).
-The result is a static table (dn_step_set_bounds); outputs do not depend on it.
+With an equal split every SM streams the same bytes, yet the rate at which an SM can pull its share
+out of HBM differs persistently between SMs (position relative to the two dies / HBM stacks:
+profiles/r01_step_phase_times*.txt show the same SMs 15-20 % slower in every layer), and every grid
+barrier waits for the slowest.  ``calibrate`` runs a few decode steps with the kernel's phase stamps
+on (TMEM parking off, so every SM starts a phase with the same pre-filled bytes), converts each SM's
+gate/up + down consume time into one speed per SM, re-partitions the rows of all four phases
+proportionally (damped, a few rounds), and keeps the table only if a timed A/B says the step got
+faster.  The result is static (dn_step_set_bounds); outputs do not depend on it.
 """
 from __future__ import annotations
 
@@ -24,7 +26,24 @@ def _equal_bounds(rows: int, align: int, sms: int) -> np.ndarray:
     return np.array([(units * i) // sms * align for i in range(sms + 1)], dtype=np.int64)
 
 
-def calibrate(rt, nonce: str = "__calib__", rounds: int = 3, steps_per_round: int = 2, damping: float = 0.6) -> List[np.ndarray]:
+_DBG_WORDS = 32          # MK_DBG_WORDS
+
+
+def _time_steps(rt, step, n: int = 12) -> float:
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        step()
+    with torch.cuda.stream(rt.compute_stream):
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def calibrate(rt, nonce: str = "__calib__", rounds: int = 3, steps_per_round: int = 2, damping: float = 0.7) -> List[np.ndarray]:
     """Calibrate ``rt.model``'s partition using decode steps on a scratch nonce (KV content is
     irrelevant).  Requires a loaded fit-mode runtime whose layers are bound."""
     lib = _cabi.load()
@@ -48,47 +67,56 @@ def calibrate(rt, nonce: str = "__calib__", rounds: int = 3, steps_per_round: in
         from dnet_b200.shard.policies import _cuda_common as cc
         cc.wait_layers_ready(rt, pol.weight_cache, run)
         model.load_weights(list(to_bind.items()), strict=False)
-    bounds = [_equal_bounds(rows[i], align[i], sms) for i in range(4)]
+    equal = [_equal_bounds(rows[i], align[i], sms) for i in range(4)]
+    bounds = [b.copy() for b in equal]
     arr = (C.c_int32 * len(run))(*run)
     s = rt.compute_stream_ptr
-    buf = (C.c_uint64 * (sms * L * 16))()
+    buf = (C.c_uint64 * (sms * L * _DBG_WORDS))()
 
     def step():
         _cabi.check(lib.dn_shard_step(model._h, arr, L, ns.x1.data_ptr(), ns.kv._h, 0, 0, None, None, None, 1, s))
 
-    for _ in range(2):
-        step()
+    def apply(bs):
+        tbl = np.concatenate(bs).astype(np.int32)
+        _cabi.check(lib.dn_step_set_bounds(model._h, tbl.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    apply(equal)
+    t_equal = _time_steps(rt, step)
+    weight = np.ones(sms)                       # relative share of each SM
     for _ in range(rounds):
+        lib.dn_set_option(b"park", 0)
         lib.dn_set_option(b"mk_debug", 1)
-        dur = np.zeros((4, sms))
+        dur = np.zeros(sms)
         for _ in range(steps_per_round):
             step()
             rt.compute_stream.synchronize()
-            n = lib.dn_step_debug(model._h, buf, sms * L * 16, s)
-            a = np.frombuffer(buf, dtype=np.uint64).reshape(sms, L, 16).astype(np.int64)
+            lib.dn_step_debug(model._h, buf, sms * L * _DBG_WORDS, s)
+            a = np.frombuffer(buf, dtype=np.uint64).reshape(sms, L, _DBG_WORDS).astype(np.int64)
             lo = min(2, L - 1)
-            for ph, (i0, i1) in enumerate(_STAMP_PAIRS):
-                dur[ph] += (a[:, lo:, i1] - a[:, lo:, i0]).mean(axis=1)
+            for (i0, i1) in _STAMP_PAIRS[2:]:                 # gate/up and down: 85 % of the bytes
+                dur += (a[:, lo:, i1] - a[:, lo:, i0]).mean(axis=1)
         lib.dn_set_option(b"mk_debug", 0)
-        flat = []
+        lib.dn_set_option(b"park", 1)
+        got = sum(np.diff(bounds[ph]) * (cfg["hidden_size"] if ph == 2 else cfg["intermediate_size"]) for ph in (2, 3)).astype(np.float64)
+        speed = got / np.maximum(dur, 1.0)
+        target = speed / speed.mean()
+        weight = (1.0 - damping) * weight + damping * target
+        weight /= weight.mean()
         for ph in range(4):
-            if ph < 2:
-                # QKV / O are short phases that start with a pre-filled ring: their time is not
-                # proportional to rows, so only GATE/UP and DOWN (85% of the bytes) are re-partitioned
-                flat.append(bounds[ph])
-                continue
-            units = np.diff(bounds[ph]) // align[ph]
-            speed = units / np.maximum(dur[ph], 1.0)
-            target = speed / speed.sum() * units.sum()
-            new = (1.0 - damping) * units + damping * target
+            total = rows[ph] // align[ph]
+            new = weight / weight.sum() * total
             iu = np.floor(new).astype(np.int64)
-            rem = int(units.sum() - iu.sum())
+            rem = int(total - iu.sum())
             order = np.argsort(-(new - iu))
             iu[order[:rem]] += 1
             bounds[ph] = np.concatenate([[0], np.cumsum(iu)]) * align[ph]
             assert bounds[ph][-1] == rows[ph]
-            flat.append(bounds[ph])
-        tbl = np.concatenate(flat).astype(np.int32)
-        _cabi.check(lib.dn_step_set_bounds(model._h, tbl.ctypes.data_as(C.POINTER(C.c_int32))))
+        apply(bounds)
+    t_cal = _time_steps(rt, step)
+    if t_cal >= t_equal:                         # no gain on this GPU: keep the equal split
+        apply(equal)
+        bounds = equal
+    rt.calibration = {"ms_equal": t_equal, "ms_calibrated": t_cal, "kept": bool(t_cal < t_equal),
+                      "share_min": float(weight.min()), "share_max": float(weight.max())}
     rt.release_nonce(nonce)
     return bounds
