@@ -264,6 +264,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         lib.dn_set_option(b"attn_chunk", args.attn_chunk)
     if args.inflight >= 0:
         lib.dn_set_option(b"inflight", args.inflight)
+    if args.inflight_hi >= 0:
+        lib.dn_set_option(b"inflight_hi", args.inflight_hi)
     if args.park >= 0:
         lib.dn_set_option(b"park", args.park)
     pol = rt.policy
@@ -466,6 +468,7 @@ def main():
     ap.add_argument("--l2-prefetch-kb", type=int, default=64)
     ap.add_argument("--prompt-len", type=int, default=128)
     ap.add_argument("--mk-flags", type=int, default=0)
+    ap.add_argument("--inflight-hi", type=int, default=-1)
     ap.add_argument("--park", type=int, default=-1, help="step kernel: TMEM parking of ready stages during grid barriers (-1 = library default)")
     ap.add_argument("--inflight", type=int, default=-1, help="step kernel: cap on ring stages with loads outstanding (-1 = library default)")
     ap.add_argument("--attn-chunk", type=int, default=0, help="step kernel: min tokens per attention split (0 = library default)")

@@ -40,6 +40,7 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
+static int g_inflight_hi = 0;   // step kernel: in-flight cap while the consumers starve (0 = same as inflight)
 static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
 static int g_inflight = 3;      // step kernel: cap on ring stages with loads outstanding (0 = no cap); measured 2/3/4/5/none = 357/381/374/369/366 tok/s
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
@@ -247,6 +248,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
+  if (!strcmp(key, "inflight_hi")) { g_inflight_hi = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "park")) { g_park = value != 0; return DN_OK; }
   if (!strcmp(key, "inflight")) { g_inflight = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "attn_chunk")) { g_attn_chunk = value < 32 ? 32 : (int)((value + 31) / 32 * 32); return DN_OK; }
@@ -809,6 +811,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.pf_depth = g_pf_depth;
   p.attn_chunk = g_attn_chunk;
   p.inflight = g_inflight;
+  p.inflight_hi = g_inflight_hi > g_inflight ? g_inflight_hi : g_inflight;
   // TMEM parking needs one fragment geometry (seg == 1024) in every phase
   p.park = (g_park && c.hidden % 1024 == 0 && c.ffn % 1024 == 0 && (c.n_heads * HD) % 1024 == 0) ? 1 : 0;
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
@@ -839,6 +842,19 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   if (stages > MK_MAX_STAGES) stages = MK_MAX_STAGES;
   if (stages < 2) return fail(DN_EINVAL, "model too wide for the megakernel's shared-memory ring");
   p.n_stages = stages;
+  // the cap waits on the full-barrier of an earlier use of a slot: it must stay below the ring depth (parity aliasing)
+  // Safe caps with two producers taking alternate stages: the slot a producer waits on is re-armed
+  // `stages - cap` stages later; that must be its own stage (even distance) or one the other producer
+  // cannot reach first (cap <= stages/2), else the full-barrier can run two phases ahead of the waited
+  // parity and the wait only returns one ring revolution later (measured: 6 tok/s at cap 5 of 6).
+  auto safe_cap = [stages](int cap) {
+    if (cap >= stages) cap = stages - 1;
+    while (cap > stages / 2 && ((stages - cap) & 1)) --cap;
+    return cap < 0 ? 0 : cap;
+  };
+  p.inflight = safe_cap(p.inflight);
+  p.inflight_hi = safe_cap(p.inflight_hi);
+  if (p.inflight_hi < p.inflight) p.inflight_hi = p.inflight;
   p.scratch_bytes = scratch;
   const size_t smem = (size_t)stages * MK_STAGE_BYTES + scratch + tail;
   if ((size_t)g_sms > (size_t)CTAS_PER_SM * g_sms) return fail(DN_EINVAL, "head partial buffer too small");

@@ -88,6 +88,7 @@ struct MkParams {
   const int32_t* token_in;      // first shard: token id lives here (the hop slot) instead of st->token
   void* send_dst; uint32_t* send_flag; uint32_t send_seq;
   int park;                  // 1: consumer warps park ready ring stages in tensor memory while they wait at a grid barrier
+  int inflight_hi;           // cap while the consumers are starving for weights (>= inflight)
   int inflight;              // producer: at most this many ring stages with loads outstanding (0 = whole ring)
   int attn_chunk;            // minimum tokens per attention split (multiple of 32)
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
@@ -272,6 +273,7 @@ __device__ __forceinline__ void mk_range(const MkParams& p, int ph, const MkPhas
 }
 
 struct MkRing {
+  volatile unsigned int* starve;   // set by consumer warp 0 while it waits for weights (ring empty), cleared at a grid barrier
   unsigned char* data;   // n_stages * MK_STAGE_BYTES
   uint64_t* full;        // [n_stages]
   uint64_t* empty;       // [n_stages]
@@ -305,10 +307,11 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
     const bf16* src = (lane < nv) ? mk_row(p, L, ph, rb + lane, d.K) : nullptr;
     for (int sg = 0; sg < nseg; ++sg) {
       if ((int)(idx % MK_PW) == which) {
-        if (p.inflight > 0 && idx >= (unsigned)p.inflight) {
+        const int cap = (*ring.starve != 0u) ? p.inflight_hi : p.inflight;
+        if (cap > 0 && idx >= (unsigned)cap) {
           // bound the bytes in flight (not the buffered bytes): a deep queue of outstanding bulk loads
           // is what the grid barrier's polls and every staging load have to wait behind
-          const unsigned int j = idx - (unsigned)p.inflight;
+          const unsigned int j = idx - (unsigned)cap;
           mbar_wait(&ring.full[j % (unsigned)ring.n_stages], (j / (unsigned)ring.n_stages) & 1u, p.err);
         }
         mbar_wait_dbg(&ring.empty[ring.stage], ring.phase ^ 1u, p.err, accp);
@@ -446,6 +449,7 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams& p, unsigned int&
                                                 unsigned int* bar_done, int lane) {
   cbar_sync();          // every consumer thread's writes precede thread 0's release (cumulativity)
   if (threadIdx.x == 0) {
+    *ring.starve = 0u;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar_count) : "memory");
     if (!(p.flags & 8)) st_release_cta(bar_req, k + 1u);
   }
@@ -523,6 +527,7 @@ __device__ __forceinline__ void mk_consume(const MkParams& p, int ph, int li, Mk
           }
         }
       } else {
+        if (cw == 0 && !mbar_test_wait(&ring.full[ring.stage], ring.phase)) { if (lane == 0) *ring.starve = 1u; }
         mbar_wait_dbg(&ring.full[ring.stage], ring.phase, p.err, accp);
         if (!(p.flags & 4)) {     // flags bit2: timing experiment, skip the math (results are garbage)
           const uint32_t a_base = ring_base + (uint32_t)ring.stage * MK_STAGE_BYTES + a_lane;
@@ -821,6 +826,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   float* red = reinterpret_cast<float*>(ring.empty + MK_MAX_STAGES);   // [64] misc scratch
   ring.stage = 0;
   ring.phase = 0;
+  ring.starve = reinterpret_cast<volatile unsigned int*>(red + 60);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -836,7 +842,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   unsigned int* tmem_slot = reinterpret_cast<unsigned int*>(red + 56);
   unsigned int* bar_req = reinterpret_cast<unsigned int*>(red + 57);
   unsigned int* bar_done = reinterpret_cast<unsigned int*>(red + 58);
-  if (threadIdx.x == 0) { *consumed = 0u; *bar_req = 0u; *bar_done = 0u; *tmem_slot = 0u; }
+  if (threadIdx.x == 0) { *consumed = 0u; *bar_req = 0u; *bar_done = 0u; *tmem_slot = 0u; red[60] = 0.f; }
   if (p.park && warp == 0) {
     // all 512 TMEM columns: 8 consumer warps x 8 parked stages x 32 columns (one CTA per SM, so nothing else wants them)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");

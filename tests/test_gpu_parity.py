@@ -160,6 +160,48 @@ def test_every_step_logits_within_tolerance(tiny):
         rt.unload_model_core()
 
 
+@pytest.mark.gpu
+def test_tmem_parking_and_inflight_cap_do_not_change_results(cuda_lib):
+    """Where a weight stage waits (shared-memory ring or parked in tensor memory during a grid
+    barrier) and how many loads are outstanding are scheduling choices: tokens, logprobs and logits
+    must be bit-identical.  Full width (seg == 1024 in every phase), otherwise parking is off."""
+    from dnet_b200.shard.models import ShardLoadModelRequest
+    from dnet_b200.shard.runtime import ShardRuntime
+    from dnet_b200.utils.model import SyntheticSource
+
+    cfgd = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=8, head_dim=128, intermediate_size=14336,
+                vocab_size=128256, num_hidden_layers=2, rms_norm_eps=1e-5, rope_theta=500000.0, model_type="llama",
+                tie_word_embeddings=False, torch_dtype="bfloat16")
+    src = SyntheticSource(cfgd, seed=3)
+    prompt = np.random.Generator(np.random.PCG64(77)).integers(0, 128256, size=70).tolist()
+    rt = ShardRuntime(shard_id="park")
+    rt.kv_cache_config.max_tokens = 256
+    rt.load_model_core(ShardLoadModelRequest(model_path=src, total_layers=2, layers=[0, 1], window_size=2, residency_size=2,
+                                             kv_bits="fp16"))
+    assert rt.use_megakernel
+    base = None
+    try:
+        for i, (park, infl, hi) in enumerate([(1, 3, 0), (0, 3, 0), (1, 0, 0), (1, 2, 6), (0, 0, 0)]):
+            cuda_lib.dn_set_option(b"park", park)
+            cuda_lib.dn_set_option(b"inflight", infl)
+            cuda_lib.dn_set_option(b"inflight_hi", hi)
+            nonce = f"n{i}"
+            out = ring_generate([rt], nonce, prompt, 12)
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce[nonce].x1)
+            torch.cuda.synchronize()
+            assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+            cur = ([t for t, _, _ in out], [p for _, p, _ in out], f32.cpu())
+            if base is None:
+                base = cur
+            else:
+                assert cur[0] == base[0] and cur[1] == base[1] and torch.equal(cur[2], base[2]), (park, infl, hi)
+    finally:
+        cuda_lib.dn_set_option(b"park", 1)
+        cuda_lib.dn_set_option(b"inflight", 3)
+        cuda_lib.dn_set_option(b"inflight_hi", 0)
+        rt.unload_model_core()
+
+
 @pytest.mark.parametrize("via_bytes", [False, True])
 def test_two_shards_bit_identical_to_one(tiny, via_bytes):
     """device hand-off (NVLink hop path) and wire bytes (gRPC path) both reproduce the
