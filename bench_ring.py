@@ -362,7 +362,10 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                     "busiest_shard_bytes": slow, "pipelined_roofline_tok_s": peak * 1e9 / slow,
                     "single_sequence": {"tok_s": 1e3 / single_ms, "ms_per_token": single_ms,
                                         "roofline_tok_s": peak * 1e9 / tb, "frac": (1e3 / single_ms) / (peak * 1e9 / tb),
-                                        "per_rank_compute_ms": comp_ms, "ring_hop_us": hop_us}}
+                                        "per_rank_compute_ms": comp_ms, "ring_hop_us": hop_us,
+                                        "ring_hop_note": "(one sequence's round trip - sum of the shards' stand-alone step times) / shards; "
+                                                         "negative = the hop is hidden: a waiting shard's step kernel already streams its first "
+                                                         "weight stages while it spins on the predecessor's flag"}}
         out = {
             "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
