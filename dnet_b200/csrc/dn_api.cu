@@ -88,8 +88,9 @@ struct LayerW {
   bool tm_ok = false;
 };
 
-constexpr int TPF_MAX = 128;   // tokens per tensor-core prefill chunk
+constexpr int TPF_MAX = 512;   // tokens per tensor-core prefill chunk (weights are streamed once per chunk)
 static int g_tc_prefill = 1;
+static int g_tc_attn = 1;      // prefill attention on tcgen05 (GQA groups dividing 128), else the CUDA-core kernel
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -141,6 +142,8 @@ struct dn_model {
   // tensor-core prefill scratch ([TPF_MAX][...]) and the TMA descriptors of the activation buffers
   bf16 *pf_xn = nullptr, *pf_qkv = nullptr, *pf_q = nullptr, *pf_attn = nullptr, *pf_h = nullptr, *pf_act = nullptr;
   CUtensorMap tm_xn[3], tm_attn[3], tm_act[3];   // token-tile boxes of 32 / 64 / 128 rows
+  std::vector<CUtensorMap> tm_kv;                // per local layer: KV pool as [pages*2*n_kv*64 rows][128] bf16, box 64 x 64
+  bool tm_kv_ok = false;
   bool pf_ok = false;
   unsigned long long* mk_dbg = nullptr;
   size_t mk_dbg_words = 0;
@@ -218,6 +221,9 @@ static cudaError_t init_kernel_attrs() {
   PRE(k_attn<1>) PRE(k_attn<2>) PRE(k_attn<4>) PRE(k_attn<5>) PRE(k_attn<7>) PRE(k_attn<8>)
   PRE(k_shard_step<1>) PRE(k_shard_step<2>) PRE(k_shard_step<4>) PRE(k_shard_step<5>) PRE(k_shard_step<7>) PRE(k_shard_step<8>)
 #undef PRE
+#define ATA(Gv) if ((e = cudaFuncSetAttribute(k_attn_prefill_tc<Gv>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)) != cudaSuccess) return e;
+  ATA(1) ATA(2) ATA(4) ATA(8)
+#undef ATA
   return cudaSuccess;
 }
 
@@ -247,6 +253,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "tc_attn")) { g_tc_attn = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
   if (!strcmp(key, "inflight_hi")) { g_inflight_hi = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "park")) { g_park = value != 0; return DN_OK; }
@@ -311,6 +318,15 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
       dn_model_destroy(m);
       return DN_ENOMEM;
     }
+  }
+  if (m->kv_pool) {
+    // never-written rows must be finite: the tcgen05 attention multiplies masked P (= 0) with whatever V holds
+    CK(cudaMemset(m->kv_pool, 0, m->layer_elems * n_layers * 2));
+    m->tm_kv.resize(n_layers);
+    m->tm_kv_ok = true;
+    const long long rows = (long long)cfg->kv_pool_pages * 2 * cfg->n_kv_heads * PAGE;
+    for (int i = 0; i < n_layers && m->tm_kv_ok; ++i)
+      m->tm_kv_ok = rows < (1ll << 31) && make_tmap(&m->tm_kv[i], m->kv_pool + (size_t)i * m->layer_elems, (int)rows, HD, PAGE) == DN_OK;
   }
   for (int p = cfg->kv_pool_pages - 1; p >= 0; --p) m->free_pages.push_back(p);
   m->mk_host.resize(n_layers > 0 ? n_layers : 1);
@@ -591,7 +607,17 @@ static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* k
   k_rope_append<<<dim3(c.n_heads + 2 * c.n_kv_heads, T), 128, 0, s>>>(m->pf_qkv, m->pf_q, pool, kv->block_table, kv->st, m->inv_freq,
                                                                         c.n_heads, c.n_kv_heads);
   g_launches++;
-  {
+  if (g_tc_attn && m->tm_kv_ok && (m->G == 1 || m->G == 2 || m->G == 4 || m->G == 8)) {
+    AtParams a;
+    a.q = m->pf_q; a.out = m->pf_attn; a.block_table = kv->block_table; a.st = kv->st;
+    a.n_heads = c.n_heads; a.n_kv = c.n_kv_heads; a.T = T; a.err = err;
+    const int tb = 128 / m->G;
+    dim3 grid(c.n_kv_heads, (T + tb - 1) / tb);
+#define PFT(Gv) case Gv: k_attn_prefill_tc<Gv><<<grid, 256, AT_SMEM, s>>>(m->tm_kv[li], a); break;
+    switch (m->G) { PFT(1) PFT(2) PFT(4) PFT(8) default: break; }
+#undef PFT
+    g_launches++;
+  } else {
     dim3 grid(c.n_kv_heads, (T + 3) / 4);
 #define PFA(Gv) case Gv: k_attn_prefill<Gv, 4><<<grid, Gv * 32, 0, s>>>(m->pf_q, pool, kv->block_table, kv->st, m->pf_attn, c.n_heads, c.n_kv_heads, T); break;
     switch (m->G) { PFA(1) PFA(2) PFA(4) PFA(5) PFA(7) PFA(8) default: return fail(DN_EINVAL, "GQA group unsupported"); }

@@ -131,7 +131,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles, tt = tile / n_tiles;
+        const int tt = tile % t_tiles, nt = tile / t_tiles;     // token tiles of one weight tile run back to back (weights hit L2)
         for (int ks = 0; ks < k_steps; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1u, p.err);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
@@ -175,7 +175,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
     const int ew = warp - 4;                          // TMEM lanes [32 ew, 32 ew + 32)
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % n_tiles, tt = tile / n_tiles;
+      const int tt = tile % t_tiles, nt = tile / t_tiles;     // token tiles of one weight tile run back to back (weights hit L2)
       const int n = nt * TC_BM + ew * 32 + lane;      // output feature owned by this thread
       mbar_wait(tmem_full, acc_phase, p.err);
       tc_fence_after();
@@ -378,6 +378,247 @@ __global__ void __launch_bounds__(G * 32) k_attn_prefill(const bf16* __restrict_
 #pragma unroll
     for (int dd = 0; dd < 4; ++dd) ob[dd] = __float2bfloat16_rn(o[qi][dd] * invL);
     *reinterpret_cast<uint2*>(out + (size_t)(t0 + qi) * n_heads * HD + head * HD + lane * 4) = *reinterpret_cast<const uint2*>(ob);
+  }
+}
+
+
+// =================================================================================================
+// causal prefill attention on tcgen05 (flash-attention forward over the paged KV)
+//
+// CTA = (kv head, block of TB = 128/G query tokens): the 128 MMA rows are the G query heads of the
+// group x TB tokens (row = g*TB + t), so one K/V tile serves the whole GQA group.
+//   S  = Q . K^T      A = Q [128 x 128 d] (K-major, written once with the 128B swizzle),
+//                     B = K tile [128 tokens x 128 d] (K-major, TMA SWIZZLE_128B, 2 pages)
+//   O += P . V        A = P [128 x 128 tokens] (K-major, written by the softmax threads),
+//                     B = V tile [128 tokens x 128 d] as MN-major operand (rows = k), same TMA boxes
+// Accumulators live in TMEM (S: columns 0-127, P.V: columns 128-255); the 128 softmax threads own
+// one row each (TMEM lane = row): fp32 scores, causal mask, online max / sum exactly as the
+// CUDA-core kernel, and the running output o[128] stays in registers (o = o*corr + P.V per tile),
+// so nothing is read-modify-written in TMEM.  P is fed to the tensor core as P_hi + P_lo (two bf16
+// terms, 16 mantissa bits): the oracle keeps P in fp32, and a single bf16 P would add a rounding
+// point the reference does not have.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = softmax.
+// =================================================================================================
+struct AtParams {
+  const bf16* q;                 // [T][n_heads][128] (RoPE applied, unscaled)
+  bf16* out;                     // [T][n_heads][128]
+  const int32_t* block_table;
+  const StepState* st;
+  int n_heads, n_kv, T;
+  unsigned int* err;
+};
+
+// MN-major, SWIZZLE_128B operand: 64 contiguous elements along N per 128-byte row, 8 k-rows per
+// 1024-byte atom; LBO = bytes between N atoms (dims 0-63 -> 64-127), SBO = bytes between k groups
+__device__ __forceinline__ uint64_t tc_smem_desc_mn(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// byte offset of the 16-byte chunk (row r, chunk c of 16) inside a [2 halves][128 rows][128 B] swizzled tile
+__device__ __forceinline__ uint32_t at_swz(int r, int c) {
+  return (uint32_t)((c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+}
+
+constexpr int AT_TILE = 128 * 128 * 2;     // one [128 x 128] bf16 tile = 32 KiB (two 64-column halves)
+constexpr int AT_SMEM = 5 * AT_TILE + 1024 + 256;
+
+template <int G>
+__global__ void __launch_bounds__(256, 1) k_attn_prefill_tc(const __grid_constant__ CUtensorMap mapKV, const AtParams p) {
+  constexpr int TB = 128 / G;
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sQ = smem;
+  unsigned char* sK = smem + AT_TILE;
+  unsigned char* sV = smem + 2 * AT_TILE;
+  unsigned char* sPh = smem + 3 * AT_TILE;
+  unsigned char* sPl = smem + 4 * AT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * AT_TILE);
+  uint64_t *k_full = bars, *k_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3, *s_full = bars + 4, *s_empty = bars + 5,
+           *p_full = bars + 6, *pv_full = bars + 7, *pv_empty = bars + 8;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvh = blockIdx.x, t0 = blockIdx.y * TB;
+  const int pos0 = p.st->pos;
+  const int nq = min(TB, p.T - t0);                         // query tokens of this CTA
+  const int kv_max = pos0 + t0 + nq;                        // keys visible to its last query
+  const int n_tiles = (kv_max + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // Q tile: rows (g, t) <- q[t0 + t][kvh*G + g][:], zero rows beyond the chunk; written with the TMA 128B swizzle
+  for (int i = threadIdx.x; i < 128 * 16; i += 256) {
+    const int r = i >> 4, c = i & 15;
+    const int g = r / TB, t = r % TB;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (g < G && t < nq) v = *reinterpret_cast<const uint4*>(p.q + ((size_t)(t0 + t) * p.n_heads + kvh * G + g) * HD + c * 8);
+    *reinterpret_cast<uint4*>(sQ + at_swz(r, c)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tS = tmem_base, tPV = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = (uint32_t)(j & 1);
+        const int np = (kv_max + PAGE - 1) / PAGE;
+        const int pg0 = p.block_table[2 * j];
+        const int pg1 = (2 * j + 1 < np) ? p.block_table[2 * j + 1] : pg0;     // unused half: any valid page (masked)
+        const int rk0 = ((pg0 * 2 + 0) * p.n_kv + kvh) * PAGE, rk1 = ((pg1 * 2 + 0) * p.n_kv + kvh) * PAGE;
+        const int rv0 = ((pg0 * 2 + 1) * p.n_kv + kvh) * PAGE, rv1 = ((pg1 * 2 + 1) * p.n_kv + kvh) * PAGE;
+        mbar_wait(k_empty, ph ^ 1u, p.err);
+        mbar_arrive_expect_tx(k_full, AT_TILE);
+        tma_load_2d(sK, &mapKV, 0, rk0, k_full);
+        tma_load_2d(sK + 16384, &mapKV, 64, rk0, k_full);
+        tma_load_2d(sK + 8192, &mapKV, 0, rk1, k_full);
+        tma_load_2d(sK + 16384 + 8192, &mapKV, 64, rk1, k_full);
+        mbar_wait(v_empty, ph ^ 1u, p.err);
+        mbar_arrive_expect_tx(v_full, AT_TILE);
+        tma_load_2d(sV, &mapKV, 0, rv0, v_full);
+        tma_load_2d(sV + 16384, &mapKV, 64, rv0, v_full);
+        tma_load_2d(sV + 8192, &mapKV, 0, rv1, v_full);
+        tma_load_2d(sV + 16384 + 8192, &mapKV, 64, rv1, v_full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = tc_instr_desc(128, 128);
+      const uint32_t idesc_pv = tc_instr_desc(128, 128) | (1u << 16);       // B operand MN-major
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = (uint32_t)(j & 1);
+        // ---- S = Q K^T
+        mbar_wait(k_full, ph, p.err);
+        mbar_wait(s_empty, ph ^ 1u, p.err);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t adesc = tc_smem_desc(sQ + h * 16384), bdesc = tc_smem_desc(sK + h * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma(tS, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (h | k) ? 1u : 0u);
+        }
+        tc_commit(k_empty);
+        tc_commit(s_full);
+        // ---- PV = (P_hi + P_lo) V
+        mbar_wait(p_full, ph, p.err);
+        mbar_wait(v_full, ph, p.err);
+        mbar_wait(pv_empty, ph ^ 1u, p.err);
+        tc_fence_after();
+        const uint64_t vdesc = tc_smem_desc_mn(sV, 16384, 1024);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const unsigned char* sP = part ? sPl : sPh;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t adesc = tc_smem_desc(sP + (kk >> 2) * 16384) + (uint64_t)(2 * (kk & 3));
+            tc_mma(tPV, adesc, vdesc + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (part | kk) ? 1u : 0u);
+          }
+        }
+        tc_commit(v_empty);
+        tc_commit(pv_full);
+      }
+    }
+  } else if (warp >= 4) {
+    const int qd = warp - 4;                           // TMEM lane quarter
+    const int r = qd * 32 + lane;                      // this thread's row
+    const int g = r / TB, t = r % TB;
+    const bool row_ok = g < G && t < nq;
+    const int limit = pos0 + t0 + t;                   // last visible key position (causal)
+    const float scale = 0.08838834764831845f;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) o[i] = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      const int tok0 = j << 7;
+      mbar_wait(s_full, ph, p.err);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float v[16];
+        tc_ld16(tS + lane_off + c * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool vis = row_ok && (tok0 + c * 16 + i) <= limit;
+          mx = fmaxf(mx, vis ? v[i] * scale : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float corr = (m_new == -INFINITY) ? 1.0f : exp2f((m - m_new) * LOG2E);
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float v[16];
+        tc_ld16(tS + lane_off + c * 16, v);
+        __align__(16) bf16 hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool vis = row_ok && (tok0 + c * 16 + i) <= limit;
+          const float pe = vis ? exp2f((v[i] * scale - m_new) * LOG2E) : 0.f;
+          lsum += pe;
+          hi[i] = __float2bfloat16_rn(pe);
+          lo[i] = __float2bfloat16_rn(pe - __bfloat162float(hi[i]));
+        }
+        *reinterpret_cast<uint4*>(sPh + at_swz(r, 2 * c)) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(sPh + at_swz(r, 2 * c + 1)) = *reinterpret_cast<const uint4*>(hi + 8);
+        *reinterpret_cast<uint4*>(sPl + at_swz(r, 2 * c)) = *reinterpret_cast<const uint4*>(lo);
+        *reinterpret_cast<uint4*>(sPl + at_swz(r, 2 * c + 1)) = *reinterpret_cast<const uint4*>(lo + 8);
+      }
+      l = l * corr + lsum;
+      m = m_new;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(p_full); mbar_arrive(s_empty); }
+      mbar_wait(pv_full, ph, p.err);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v[16];
+        tc_ld16(tPV + lane_off + c * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c * 16 + i] = fmaf(o[c * 16 + i], corr, v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pv_empty);
+    }
+    if (row_ok) {
+      const float invL = 1.0f / l;
+      bf16* dst = p.out + ((size_t)(t0 + t) * p.n_heads + kvh * G + g) * HD;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        __align__(16) bf16 ob[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ob[i] = __float2bfloat16_rn(o[c * 8 + i] * invL);
+        *reinterpret_cast<uint4*>(dst + c * 8) = *reinterpret_cast<const uint4*>(ob);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
 }
 

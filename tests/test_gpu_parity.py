@@ -463,7 +463,7 @@ def test_tensor_core_prefill_matches_gemv_prefill(tiny, cuda_lib):
         cuda_lib.dn_set_option(b"tc_prefill", tc)
         rt = make_runtime(cfgd, w, range(L))
         try:
-            assert rt.model.max_prefill_chunk == (128 if tc else 0)
+            assert rt.model.max_prefill_chunk == (512 if tc else 0)
             rt.policy.process(token_message(rt, "p", prompt))
             res = rt.activation_send_queue.get_nowait()
             f32, _ = rt.model.head_logits(rt._kv_by_nonce["p"].x_view(len(prompt)))
@@ -488,6 +488,43 @@ def test_tensor_core_prefill_matches_gemv_prefill(tiny, cuda_lib):
     top2 = torch.topk(ref, 2).values
     if float(top2[0] - top2[1]) > 0.05:
         assert outs[1][0][0] == outs[0][0][0] == int(torch.argmax(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny_llama", "tiny_qwen2_tied"])
+@pytest.mark.parametrize("plen", [16, 45, 128, 129, 200, 333, 700])
+def test_tcgen05_attention_matches_cuda_core_attention(cuda_lib, name, plen):
+    """Prefill attention on tcgen05 (S and P.V in TMEM, P as hi+lo bf16) against the CUDA-core
+    kernel on the same prompt: every chunk boundary / page boundary / causal edge; the two only
+    differ in fp32 summation order, so the last-position logits agree far inside the bf16 envelope
+    and the greedy continuation is the same."""
+    g = load_golden(name)
+    w = oracle_weights(g["config"], g["wseed"])
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+    prompt = np.random.Generator(np.random.PCG64(900 + plen)).integers(0, cfgd["vocab_size"], size=plen).tolist()
+    outs = {}
+    try:
+        for tc in (1, 0):
+            cuda_lib.dn_set_option(b"tc_attn", tc)
+            rt = make_runtime(cfgd, w, range(L), max_tokens=1024)
+            try:
+                rt.policy.process(token_message(rt, "p", prompt))
+                res = rt.activation_send_queue.get_nowait()
+                f32, _ = rt.model.head_logits(rt._kv_by_nonce["p"].x_view(len(prompt)))
+                torch.cuda.synchronize()
+                assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+                outs[tc] = (res.token_id, f32.cpu())
+            finally:
+                rt.unload_model_core()
+    finally:
+        cuda_lib.dn_set_option(b"tc_attn", 1)
+    a, b = outs[1][1], outs[0][1]
+    assert torch.isfinite(a).all()
+    assert rel_inf(a, b) <= max(e2e_tol(g), 5e-3), rel_inf(a, b)     # two valid summation orders of a bf16 pipeline
+    top2 = torch.topk(b, 2).values
+    if float(top2[0] - top2[1]) > 0.05:
+        assert outs[1][0] == outs[0][0]
 
 
 def test_calibrated_partition_does_not_change_results(tiny, cuda_lib):
@@ -530,10 +567,10 @@ def test_calibrated_partition_does_not_change_results(tiny, cuda_lib):
             rt.unload_model_core()
 
 
-@pytest.mark.parametrize("plen", [1, 2, 3, 15, 16, 17, 33, 63, 64, 65, 127, 128, 129, 200])
+@pytest.mark.parametrize("plen", [1, 2, 3, 15, 16, 17, 33, 63, 64, 65, 127, 128, 129, 200, 511, 512, 513, 530, 700])
 def test_prompt_length_edges_against_oracle(tiny, cuda_lib, plen):
     """Ragged prompt lengths around every chunking boundary (GEMV chunks of 1/2/4, tensor-core chunks
-    of 16..128 with 32/64/128-token tiles and out-of-bounds token rows, 64-token KV pages): prefill
+    of 16..512 with 32/64/128-token tiles and out-of-bounds token rows, 64-token KV pages): prefill
     logits vs the oracle on the same prompt, then two decode steps that read the KV it wrote."""
     from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
     g, w = tiny
@@ -542,7 +579,7 @@ def test_prompt_length_edges_against_oracle(tiny, cuda_lib, plen):
     prompt = np.random.Generator(np.random.PCG64([plen, 9])).integers(0, cfgd["vocab_size"], size=plen).tolist()
     orc = LlamaOracle(OracleConfig.from_dict(cfgd), w, exact_linear=True)
     kv = {l: OracleKV() for l in range(L)}
-    rt = make_runtime(cfgd, w, range(L), max_tokens=256)
+    rt = make_runtime(cfgd, w, range(L), max_tokens=1024)
     try:
         ids = prompt
         for step in range(3):
