@@ -76,7 +76,16 @@ typedef struct dn_model_cfg {
 int dn_init(int device);                         /* cudaSetDevice + capability check (sm_100) */
 const char* dn_last_error(void);
 const char* dn_version(void);
-int dn_set_option(const char* key, int64_t value); /* "pdl" (0/1), "l2_prefetch_kb" */
+int dn_set_option(const char* key, int64_t value);
+/* process-wide tuning / experiment switches; results never depend on them:
+ *   "pdl" 0/1 (per-op path: programmatic dependent launch)   "l2_prefetch_kb" (per-op path)
+ *   "tc_prefill" 0/1  tensor-core prefill chunks of 16..512 tokens (default 1)
+ *   "tc_attn" 0/1     prefill attention on tcgen05 instead of CUDA cores (default 1)
+ *   step kernel: "park" 0/1 TMEM parking during grid barriers (1), "inflight" ring stages with loads
+ *   outstanding (3), "inflight_hi" cap while the consumers starve (0 = same), "attn_chunk" tokens per
+ *   warp before a head is split over a second CTA (32), "pf_depth" L2 look-ahead stages (0),
+ *   "mk_debug" 0/1 phase stamps for dn_step_debug, "mk_flags" timing experiments (bit2 skip math,
+ *   bit3 skip grid barriers: garbage results) */
 int64_t dn_launch_count(void);                   /* kernels launched by this library so far
                                                     (graph replays count their nodes) */
 int dn_device_sm_count(void);
