@@ -40,9 +40,9 @@ static std::atomic<long long> g_launches{0};
 static int g_pdl = 0;
 static int g_l2_prefetch_kb = 64;
 static int g_mk_flags = 0;
-static int g_inflight_hi = 0;   // step kernel: in-flight cap while the consumers starve (0 = same as inflight)
+static int g_inflight_hi = 3;   // step kernel: cap while the consumers are starving for weights
 static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
-static int g_inflight = 3;      // step kernel: cap on ring stages with loads outstanding (0 = no cap); measured 2/3/4/5/none = 357/381/374/369/366 tok/s
+static int g_inflight = 2;      // step kernel: ring stages with loads outstanding while the consumers are not starving (barriers, staging); measured caps 2/3/4/5/none = 357/381/374/369/366 tok/s static, 2-when-idle/3-when-starving +0.7 % on top
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
 static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,

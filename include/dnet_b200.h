@@ -82,7 +82,7 @@ int dn_set_option(const char* key, int64_t value);
  *   "tc_prefill" 0/1  tensor-core prefill chunks of 16..512 tokens (default 1)
  *   "tc_attn" 0/1     prefill attention on tcgen05 instead of CUDA cores (default 1)
  *   step kernel: "park" 0/1 TMEM parking during grid barriers (1), "inflight" ring stages with loads
- *   outstanding (3), "inflight_hi" cap while the consumers starve (0 = same), "attn_chunk" tokens per
+ *   outstanding (2), "inflight_hi" cap while the consumers starve for weights (3), "attn_chunk" tokens per
  *   warp before a head is split over a second CTA (32), "pf_depth" L2 look-ahead stages (0),
  *   "mk_debug" 0/1 phase stamps for dn_step_debug, "mk_flags" timing experiments (bit2 skip math,
  *   bit3 skip grid barriers: garbage results) */

@@ -197,8 +197,8 @@ def test_tmem_parking_and_inflight_cap_do_not_change_results(cuda_lib):
                 assert cur[0] == base[0] and cur[1] == base[1] and torch.equal(cur[2], base[2]), (park, infl, hi)
     finally:
         cuda_lib.dn_set_option(b"park", 1)
-        cuda_lib.dn_set_option(b"inflight", 3)
-        cuda_lib.dn_set_option(b"inflight_hi", 0)
+        cuda_lib.dn_set_option(b"inflight", 2)
+        cuda_lib.dn_set_option(b"inflight_hi", 3)
         rt.unload_model_core()
 
 
