@@ -227,6 +227,85 @@ class SyntheticSource:
         return t.cpu()
 
 
+# ---------------------------------------------------------------------------------
+# MLX group-quantised checkpoints (reference core/models/base.py:227-419: a Linear / Embedding is
+# quantised iff `<path>.scales` exists; bits / group_size come from config["quantization"] or
+# "quantization_config").  The reference turns those modules into mlx QuantizedLinear; here the
+# packed words are expanded on the host, once, while the layer record is packed:
+#     w[r, j] = scales[r, j // group] * q[r, j] + biases[r, j // group]      (fp32, one rounding to bf16)
+# with MLX's little-endian packing (element j of a row sits in word j // (32/bits) at bit
+# (j % (32/bits)) * bits).  The kernels then stream bf16 (no int8 / int4 kernels yet: the
+# checkpoint loads and runs, it does not yet run faster than bf16).
+# ---------------------------------------------------------------------------------
+_DEQUANT: Dict[str, Tuple[TensorInfo, TensorInfo, TensorInfo, int, int]] = {}
+
+
+def _quant_params(config: dict) -> Tuple[int, int]:
+    q = (config or {}).get("quantization") or (config or {}).get("quantization_config") or {}
+    bits = int(q.get("bits", 0) or 0)
+    group = int(q.get("group_size", 0) or 0)
+    return bits, group
+
+
+def _fold_quantised(tmap: Dict[str, TensorInfo], config: dict, tag: str) -> None:
+    """Replace every (`X.weight` packed, `X.scales`, `X.biases`) triple by one virtual bf16 `X.weight`."""
+    bits_cfg, group_cfg = _quant_params(config)
+    for key in [k for k in list(tmap) if k.endswith("scales")]:
+        base = key[: -len("scales")]                      # "" for embed_tokens / lm_head maps, "self_attn.q_proj." for layers
+        wk, bk = base + "weight", base + "biases"
+        if wk not in tmap or bk not in tmap:
+            raise ValueError(f"quantised tensor {tag}{base}: found scales without weight/biases")
+        w, sc, bi = tmap[wk], tmap[key], tmap[bk]
+        if w.dtype not in ("U32", "I32"):
+            raise ValueError(f"quantised tensor {tag}{wk}: packed dtype {w.dtype} unsupported")
+        # bits / group_size: the global config values when they fit the shapes, else whatever does
+        # (per-path overrides, reference base.py:283-310, show up as different shapes)
+        found = None
+        for g in dict.fromkeys([group_cfg or 64, 64, 32, 128]):
+            inf = sc.shape[-1] * g
+            if inf > 0 and (32 * w.shape[-1]) % inf == 0 and (32 * w.shape[-1]) // inf in (2, 4, 8):
+                cand = ((32 * w.shape[-1]) // inf, g)
+                if found is None or cand[0] == bits_cfg:
+                    found = cand
+                if cand[0] == bits_cfg:
+                    break
+        if found is None:
+            raise ValueError(f"quantised tensor {tag}{wk}: shapes {w.shape} / {sc.shape} fit no 2/4/8-bit packing "
+                             f"with group size 32/64/128 (3/5/6-bit packing is not supported)")
+        bits, group = found
+        in_features = sc.shape[-1] * group
+        vname = f"deq://{tag}{wk}#{len(_DEQUANT)}"
+        shape = tuple(w.shape[:-1]) + (in_features,)
+        n = 1
+        for d in shape:
+            n *= d
+        _DEQUANT[vname] = (w, sc, bi, bits, group)
+        tmap[wk] = TensorInfo("BF16", shape, n * 2, 0, vname)
+        del tmap[key], tmap[bk]
+
+
+def _fold_all_quantised(weight_info, embed_tokens, lm_head, config) -> None:
+    for lid, tmap in weight_info.items():
+        _fold_quantised(tmap, config, f"model.layers.{lid}.")
+    _fold_quantised(embed_tokens, config, "model.embed_tokens.")
+    _fold_quantised(lm_head, config, "lm_head.")
+
+
+def _dequantise(vname: str, mapped_files, source) -> torch.Tensor:
+    import numpy as np
+    w, sc, bi, bits, group = _DEQUANT[vname]
+    wq = load_weight(w, mapped_files, source).contiguous().view(torch.int32).numpy().view(np.uint32)
+    s = load_weight(sc, mapped_files, source).to(torch.float32).numpy()
+    b = load_weight(bi, mapped_files, source).to(torch.float32).numpy()
+    per = 32 // bits
+    shifts = (np.arange(per, dtype=np.uint32) * bits)[None, None, :]
+    q = ((wq[..., :, None] >> shifts) & np.uint32((1 << bits) - 1)).reshape(*wq.shape[:-1], wq.shape[-1] * per)
+    rows, cols = q.shape[-2], q.shape[-1]
+    out = q.reshape(-1, rows, cols // group, group).astype(np.float32) * s.reshape(-1, rows, cols // group, 1) \
+        + b.reshape(-1, rows, cols // group, 1)
+    return torch.from_numpy(out.reshape(*q.shape)).to(torch.bfloat16)
+
+
 def get_model_metadata(model_path) -> ModelMetadata:
     """Accepts a local directory (reference behaviour, minus the HF download), a
     HostDictSource or a SyntheticSource."""
@@ -235,6 +314,7 @@ def get_model_metadata(model_path) -> ModelMetadata:
     if isinstance(model_path, (HostDictSource, SyntheticSource)):
         src = model_path
         _classify(src.details(), weight_info, embed_tokens, lm_head, norm)
+        _fold_all_quantised(weight_info, embed_tokens, lm_head, src.config)
         _validate_layers(src.config, weight_info)
         return ModelMetadata(Path("."), dict(weight_info), embed_tokens, lm_head, norm, src.config, src)
     path = Path(model_path)
@@ -244,6 +324,7 @@ def get_model_metadata(model_path) -> ModelMetadata:
         config = json.load(f)
     for weight in sorted(glob.glob(str(path / "*.safetensors"))):
         _classify(get_safetensor_details(weight), weight_info, embed_tokens, lm_head, norm)
+    _fold_all_quantised(weight_info, embed_tokens, lm_head, config)
     _validate_layers(config, weight_info)
     return ModelMetadata(path, dict(weight_info), embed_tokens, lm_head, norm, config)
 
@@ -269,6 +350,8 @@ def load_weight(wt: TensorInfo, mapped_files: Dict[str, MappedFile], source=None
     which is the identity on the bit pattern)."""
     from .serialization import safetensor_torch_dtype
 
+    if wt.filename.startswith("deq://"):
+        return _dequantise(wt.filename, mapped_files, source)
     if wt.filename.startswith(("mem://", "syn://")):
         if source is None:
             raise ValueError("in-memory tensor needs its source")

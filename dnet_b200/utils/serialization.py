@@ -33,6 +33,7 @@ safetensor_dtype_map = {
 safetensor_torch_dtype = {
     "F32": torch.float32, "F16": torch.float16, "BF16": torch.bfloat16, "I32": torch.int32,
     "I64": torch.int64, "U8": torch.uint8, "I8": torch.int8,
+    "U32": torch.int32,      # MLX packed quantised weights: read as 32-bit words (bit pattern preserved)
 }
 
 

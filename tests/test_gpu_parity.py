@@ -602,3 +602,53 @@ def test_prompt_length_edges_against_oracle(tiny, cuda_lib, plen):
         assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
     finally:
         rt.unload_model_core()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [4, 8])
+def test_mlx_quantised_checkpoint_runs_like_its_dequantised_weights(tiny, cuda_lib, bits):
+    """A group-quantised checkpoint (packed uint32 + scales + biases, reference base.py:227-419) loaded
+    through load_model_core gives the logits / tokens of the oracle run on w = scales*q + biases."""
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+    from tests.test_host_logic import _mlx_quantise
+    g, w = tiny
+    cfgd = dict(g["config"])
+    cfgd["quantization"] = {"bits": bits, "group_size": 64}
+    L = cfgd["num_hidden_layers"]
+    packed, deq = {}, {}
+    for k, v in w.items():
+        if v.dim() == 2 and v.shape[1] % 64 == 0 and (k.endswith("proj.weight") or k.endswith("embed_tokens.weight") or k.startswith("lm_head")):
+            pk, sc, bi, q = _mlx_quantise(v.float().numpy(), bits, 64)
+            sc16, bi16 = torch.from_numpy(sc).to(torch.bfloat16), torch.from_numpy(bi).to(torch.bfloat16)
+            base = k[: -len(".weight")]
+            packed[k] = torch.from_numpy(pk.view(np.int32))
+            packed[base + ".scales"], packed[base + ".biases"] = sc16, bi16
+            ref = q.reshape(v.shape[0], -1, 64).astype(np.float32) * sc16.float().numpy()[:, :, None] + bi16.float().numpy()[:, :, None]
+            deq[k] = torch.from_numpy(ref.reshape(tuple(v.shape))).to(torch.bfloat16)
+        else:
+            packed[k] = v
+            deq[k] = v
+    prompt = g["prompt"].tolist()
+    orc = LlamaOracle(OracleConfig.from_dict(cfgd), deq, exact_linear=True)
+    kv = {l: OracleKV() for l in range(L)}
+    rt = make_runtime(cfgd, packed, range(L))
+    try:
+        ids = prompt
+        for step in range(4):
+            rt.policy.process(token_message(rt, "q", ids))
+            res = rt.activation_send_queue.get_nowait()
+            f32, _ = rt.model.head_logits(rt._kv_by_nonce["q"].x_view(len(ids)))
+            torch.cuda.synchronize()
+            x = orc.embed(torch.tensor(ids, dtype=torch.int32))
+            for l in range(L):
+                x = orc.apply_single_layer(l, x, kv[l])
+            ref = orc.lm_project(orc.normalize(x[-1:]), return_fp32=True)[0]
+            assert rel_inf(f32.cpu(), ref) <= max(e2e_tol(g), 5e-3)
+            top2 = torch.topk(ref, 2).values
+            tok_ref = int(torch.argmax(ref.to(torch.bfloat16).float()))
+            if float(top2[0] - top2[1]) > 4 * 2.0 ** -8 * float(top2[0].abs()):
+                assert res.token_id == tok_ref
+            ids = [tok_ref]
+        assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
+    finally:
+        rt.unload_model_core()

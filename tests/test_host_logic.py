@@ -254,3 +254,67 @@ def test_wire_bytes_roundtrip_is_raw_little_endian():
     assert b == np.array([0x3F80, 0x3F00, 0x4000, 0xBF80], dtype="<u2").tobytes()
     assert torch.equal(bytes_to_tensor(b, "bfloat16", (1, 2, 2)), t)
     assert torch.equal(bytes_to_tensor(b, "mlx.core.bfloat16", (4,)), t.flatten())
+
+
+def _mlx_quantise(w: np.ndarray, bits: int, group: int):
+    """affine group quantisation with MLX's packing (test-side restatement)"""
+    rows, cols = w.shape
+    g = w.reshape(rows, cols // group, group).astype(np.float32)
+    lo, hi = g.min(-1, keepdims=True), g.max(-1, keepdims=True)
+    scale = np.maximum((hi - lo) / (2 ** bits - 1), 1e-7)
+    q = np.clip(np.rint((g - lo) / scale), 0, 2 ** bits - 1).astype(np.uint32).reshape(rows, cols)
+    per = 32 // bits
+    packed = np.zeros((rows, cols // per), dtype=np.uint32)
+    for i in range(per):
+        packed |= q[:, i::per] << np.uint32(i * bits)
+    return packed, scale.reshape(rows, cols // group), lo.reshape(rows, cols // group), q
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_mlx_quantised_checkpoint_dequantises_at_load(bits):
+    """`X.scales` next to `X.weight` marks a quantised Linear / Embedding (reference base.py:227-234);
+    the loader expands it to bf16 with w = scales * q + biases and the layer record holds bf16."""
+    import torch
+    from dnet_b200.utils.layer_manager import LayerManager
+    from dnet_b200.utils.model import HostDictSource, get_model_metadata, load_weight
+
+    rng = np.random.default_rng(bits)
+    cfg = dict(hidden_size=128, num_attention_heads=1, num_key_value_heads=1, head_dim=128, intermediate_size=256, vocab_size=64,
+               num_hidden_layers=1, rms_norm_eps=1e-5, rope_theta=10000.0, model_type="llama", tie_word_embeddings=False,
+               quantization={"bits": bits, "group_size": 64})
+    shapes = {"self_attn.q_proj": (128, 128), "self_attn.k_proj": (128, 128), "self_attn.v_proj": (128, 128),
+              "self_attn.o_proj": (128, 128), "mlp.gate_proj": (256, 128), "mlp.up_proj": (256, 128), "mlp.down_proj": (128, 256)}
+    tensors, expect = {}, {}
+
+    def add(name, shape):
+        w = rng.normal(0, 0.05, size=shape).astype(np.float32)
+        packed, sc, bi, q = _mlx_quantise(w, bits, 64)
+        sc16, bi16 = torch.from_numpy(sc).to(torch.bfloat16), torch.from_numpy(bi).to(torch.bfloat16)
+        tensors[name + ".weight"] = torch.from_numpy(packed.view(np.int32))
+        tensors[name + ".scales"], tensors[name + ".biases"] = sc16, bi16
+        ref = q.reshape(shape[0], -1, 64).astype(np.float32) * sc16.float().numpy()[:, :, None] + bi16.float().numpy()[:, :, None]
+        expect[name + ".weight"] = torch.from_numpy(ref.reshape(shape)).to(torch.bfloat16)
+
+    for k, shp in shapes.items():
+        add("model.layers.0." + k, shp)
+    add("model.embed_tokens", (64, 128))
+    add("lm_head", (64, 128))
+    for k in ("model.layers.0.input_layernorm.weight", "model.layers.0.post_attention_layernorm.weight", "model.norm.weight"):
+        tensors[k] = torch.ones(128, dtype=torch.bfloat16)
+    meta = get_model_metadata(HostDictSource(tensors, cfg))
+    assert not any(k.endswith(("scales", "biases")) for k in meta.weight_info[0])
+    for suffix, info in meta.weight_info[0].items():
+        if suffix.endswith("proj.weight"):
+            assert info.dtype == "BF16" and info.shape == shapes[suffix[:-len(".weight")]]
+            got = load_weight(info, {}, meta.source)
+            assert torch.equal(got, expect["model.layers.0." + suffix])
+    assert torch.equal(load_weight(meta.embed_tokens["weight"], {}, meta.source), expect["model.embed_tokens.weight"])
+    assert torch.equal(load_weight(meta.lm_head["weight"], {}, meta.source), expect["lm_head.weight"])
+    # the packed layer record is plain bf16
+    lm = LayerManager(meta, [0])
+    assert lm.layer_bytes(0) >= sum(2 * a * b for a, b in shapes.values())
+    # a checkpoint with scales but an unsupported packing is rejected loudly
+    bad = dict(tensors)
+    bad["model.layers.0.mlp.down_proj.weight"] = torch.zeros(128, 24, dtype=torch.int32)      # 3-bit-like width
+    with pytest.raises(ValueError):
+        get_model_metadata(HostDictSource(bad, cfg))
