@@ -652,3 +652,32 @@ def test_mlx_quantised_checkpoint_runs_like_its_dequantised_weights(tiny, cuda_l
         assert cuda_lib.dn_step_error(rt.model._h, rt.compute_stream_ptr) == 0
     finally:
         rt.unload_model_core()
+
+
+@pytest.mark.gpu
+def test_quantised_kv_request_is_refused_unless_opted_in(tiny, cuda_lib, monkeypatch):
+    """The reference API defaults to kv_bits 4bit/8bit (api/models.py:316,342); a 16-bit cache gives
+    different numbers, so the request fails loudly unless DNET_KV_QUANT_FALLBACK=fp16 is set."""
+    from dnet_b200.shard.models import ShardLoadModelRequest
+    from dnet_b200.shard.runtime import ShardRuntime
+    from dnet_b200.utils.model import HostDictSource
+    g, w = tiny
+    cfgd = g["config"]
+    L = cfgd["num_hidden_layers"]
+
+    def load(rt):
+        rt.load_model_core(ShardLoadModelRequest(model_path=HostDictSource(w, cfgd), total_layers=L, layers=list(range(L)),
+                                                 window_size=L, residency_size=L, kv_bits="8bit"))
+
+    monkeypatch.delenv("DNET_KV_QUANT_FALLBACK", raising=False)
+    with pytest.raises(NotImplementedError):
+        load(ShardRuntime(shard_id="kvq"))
+    monkeypatch.setenv("DNET_KV_QUANT_FALLBACK", "fp16")
+    rt = ShardRuntime(shard_id="kvq2")
+    rt.kv_cache_config.max_tokens = 256
+    load(rt)
+    try:
+        out = ring_generate([rt], "n", g["prompt"].tolist(), 4)
+        assert [t for t, _, _ in out] == g["tokens"][:4].tolist()
+    finally:
+        rt.unload_model_core()
