@@ -232,11 +232,21 @@ class BaseRingModel(ABC):
         return bool(self._lib.dn_layer_is_bound(self._h, int(abs_layer)))
 
     def apply_quantization_from_config(self, model_config: Any, model_metadata: Any) -> bool:
-        """MLX affine group-quantised checkpoints are not handled by this build."""
+        """Reference base.py:227-419 converts modules to mlx QuantizedLinear when the checkpoint holds
+        `<path>.scales`.  Here MLX affine group-quantised tensors were already expanded to bf16 by the
+        loader (utils/model.py `_fold_quantised`), so there is nothing to convert; anything else
+        (a quantisation section whose tensors were NOT folded, e.g. another scheme) is refused."""
         q = (model_config or {}).get("quantization") or (model_config or {}).get("quantization_config")
-        if q:
-            raise NotImplementedError("quantised checkpoints are not supported by dnet_b200 yet")
-        return False
+        if not q:
+            return False
+        mode = str(q.get("mode", q.get("quant_method", "affine")) or "affine").strip().lower()
+        if mode not in ("affine", "mlx", ""):
+            raise NotImplementedError(f"quantisation mode {mode!r} is not supported (MLX affine group quantisation only)")
+        leftovers = [k for tmap in list(model_metadata.weight_info.values()) + [model_metadata.embed_tokens, model_metadata.lm_head]
+                     for k in tmap if k.endswith(("scales", "biases"))]
+        if leftovers:
+            raise NotImplementedError(f"quantised tensors were not expanded by the loader: {leftovers[:3]}")
+        return True
 
     def make_cache(self, max_tokens: int = 4096) -> KVHandle:
         return KVHandle(self, max_tokens)
