@@ -90,6 +90,7 @@ struct LayerW {
 
 constexpr int TPF_MAX = 512;   // tokens per tensor-core prefill chunk (weights are streamed once per chunk)
 static int g_tc_prefill = 1;
+static int g_gemm_bn256 = 0;   // prefill GEMMs: 256-token tiles (one accumulator set for SwiGLU); measured slower than 128-token tiles with two sets (30.7K vs 32.6K tok/s at 2048 tokens)
 static int g_tc_attn = 1;      // prefill attention on tcgen05 (GQA groups dividing 128), else the CUDA-core kernel
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -141,7 +142,7 @@ struct dn_model {
   bf16 *xa = nullptr, *xb = nullptr;
   // tensor-core prefill scratch ([TPF_MAX][...]) and the TMA descriptors of the activation buffers
   bf16 *pf_xn = nullptr, *pf_qkv = nullptr, *pf_q = nullptr, *pf_attn = nullptr, *pf_h = nullptr, *pf_act = nullptr;
-  CUtensorMap tm_xn[3], tm_attn[3], tm_act[3];   // token-tile boxes of 32 / 64 / 128 rows
+  CUtensorMap tm_xn[4], tm_attn[4], tm_act[4];   // token-tile boxes of 32 / 64 / 128 / 256 rows
   std::vector<CUtensorMap> tm_kv;                // per local layer: KV pool as [pages*2*n_kv*64 rows][128] bf16, box 64 x 64
   bool tm_kv_ok = false;
   bool pf_ok = false;
@@ -253,6 +254,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "pdl")) { g_pdl = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "l2_prefetch_kb")) { g_l2_prefetch_kb = (int)value; return DN_OK; }
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "gemm_bn256")) { g_gemm_bn256 = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "tc_attn")) { g_tc_attn = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
   if (!strcmp(key, "inflight_hi")) { g_inflight_hi = value < 0 ? 0 : (int)value; return DN_OK; }
@@ -351,7 +353,7 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
     CK(cudaMemset(m->pf_act, 0, (size_t)TPF_MAX * cfg->ffn * 2));
     m->pf_ok = (H % 128 == 0) && (qd % 128 == 0) && (cfg->ffn % 128 == 0) && ((cfg->n_kv_heads * HD) % 128 == 0) &&
                true;
-    for (int b = 0; b < 3 && m->pf_ok; ++b) {
+    for (int b = 0; b < 4 && m->pf_ok; ++b) {
       const int box = 32 << b;
       m->pf_ok = make_tmap(&m->tm_xn[b], m->pf_xn, TPF_MAX, H, box) == DN_OK &&
                  make_tmap(&m->tm_attn[b], m->pf_attn, TPF_MAX, qd, box) == DN_OK &&
@@ -570,10 +572,12 @@ static cudaError_t launch_tc(const CUtensorMap& w, const CUtensorMap& w2, const 
 // token-tile width: the widest tile that still yields >= ~100 CTAs (a 4096-row matrix has only 32
 // row tiles; narrower token tiles re-read W from L2, not from HBM -- concurrent CTAs share the tile)
 template <int EPI>
-static cudaError_t gemm_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap* x /*[3]: 32,64,128*/,
+static cudaError_t gemm_tc(const CUtensorMap& w, const CUtensorMap& w2, const CUtensorMap* x /*[4]: 32,64,128,256*/,
                            const TcParams& p, cudaStream_t s) {
   const int n_tiles = (p.N + TC_BM - 1) / TC_BM;
   auto tiles = [&](int bn) { return n_tiles * ((p.T + bn - 1) / bn); };
+  // 256-token tiles halve the L2 -> shared-memory re-reads of W at 512-token chunks (the GEMMs are L2-bound there)
+  if (g_gemm_bn256 && p.T > 128 && tiles(256) >= 100) return launch_tc<256, EPI, (EPI == EPI_SWIGLU ? 3 : 4)>(w, w2, x[3], p, s);
   if (p.T > 64 && tiles(128) >= 100) return launch_tc<128, EPI, (EPI == EPI_SWIGLU ? 4 : 6)>(w, w2, x[2], p, s);
   if (p.T > 32 && tiles(64) >= 100) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 5 : 8)>(w, w2, x[1], p, s);
   if (p.T > 32 && tiles(32) < 100 && tiles(64) * 2 > tiles(32)) return launch_tc<64, EPI, (EPI == EPI_SWIGLU ? 5 : 8)>(w, w2, x[1], p, s);

@@ -96,14 +96,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
   constexpr int A_BYTES = TC_BM * TC_BK * 2;      // 16 KB
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = NA * A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (NA * BN <= 32) ? 32 : (NA * BN <= 64) ? 64 : (NA * BN <= 128) ? 128 : (NA * BN <= 256) ? 256 : 512;
+  // two accumulator sets when they fit the 512 TMEM columns: the epilogue of tile i drains one while
+  // the MMAs of tile i+1 fill the other
+  constexpr int NACC = (2 * NA * BN <= 512) ? 2 : 1;
+  constexpr int ACC_COLS = NA * BN;
+  constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64 : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_full = empty + STAGES;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + TC_BM - 1) / TC_BM;
@@ -113,8 +117,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);     // one arrival per epilogue warp
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }   // 4: one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {                // TMEM allocation (whole warp), address lands in shared memory
@@ -147,9 +150,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = tc_instr_desc(TC_BM, BN);
-      int stage = 0; uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty, acc_phase ^ 1u, p.err);      // epilogue drained the accumulator
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ab = (NACC == 2) ? (it & 1u) : 0u;              // accumulator set of this tile
+        const uint32_t acc_phase = ((NACC == 2) ? (it >> 1) : it) & 1u;
+        const uint32_t tacc = tmem_base + ab * ACC_COLS;
+        mbar_wait(&tmem_empty[ab], acc_phase ^ 1u, p.err); // epilogue drained this accumulator set
         tc_fence_after();
         for (int ks = 0; ks < k_steps; ++ks) {
           mbar_wait(&full[stage], phase, p.err);
@@ -161,25 +168,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
             const uint64_t adesc = tc_smem_desc(sa + a * A_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle span
-              tc_mma(tmem_base + a * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+              tc_mma(tacc + a * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
           }
           tc_commit(&empty[stage]);                   // smem stage reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tmem_full);                         // accumulator complete -> epilogue
-        acc_phase ^= 1u;
+        tc_commit(&tmem_full[ab]);                    // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int ew = warp - 4;                          // TMEM lanes [32 ew, 32 ew + 32)
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int tt = tile % t_tiles, nt = tile / t_tiles;     // token tiles of one weight tile run back to back (weights hit L2)
       const int n = nt * TC_BM + ew * 32 + lane;      // output feature owned by this thread
-      mbar_wait(tmem_full, acc_phase, p.err);
+      const uint32_t ab = (NACC == 2) ? (it & 1u) : 0u;
+      const uint32_t acc_phase = ((NACC == 2) ? (it >> 1) : it) & 1u;
+      mbar_wait(&tmem_full[ab], acc_phase, p.err);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+      const uint32_t trow = tmem_base + ab * ACC_COLS + ((uint32_t)(ew * 32) << 16);
       float bias = 0.f;
       if (EPI == EPI_STORE && p.bias != nullptr && n < p.N) bias = __bfloat162float(p.bias[n]);
 #pragma unroll 1
@@ -209,8 +217,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUte
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
-      acc_phase ^= 1u;
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
     }
   }
   tc_fence_before();

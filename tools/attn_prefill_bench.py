@@ -11,6 +11,7 @@ from dnet_b200.utils.model import SyntheticSource
 from tests.helpers import token_message
 
 torch.cuda.set_device(0); _cabi.init(0); lib = _cabi.load()
+lib.dn_set_option(b"gemm_bn256", int(os.environ.get("BN256", "1")))
 cfg = dict(B.LLAMA3_8B); L = int(os.environ.get("LAYERS", cfg["num_hidden_layers"])); cfg["num_hidden_layers"] = L
 NMAX = int(os.environ.get("NMAX", "8192"))
 rt = ShardRuntime(0); rt.kv_cache_config.max_tokens = NMAX + 64
