@@ -180,6 +180,14 @@ class WeightCache:
                     self._destroy_event(old)
                 self._release_events[layer_id] = release_event
 
+    def decrease_references(self, layer_ids) -> None:
+        """decrease_reference for a whole run under one lock acquisition (decode hot path)."""
+        with self.lock:
+            rc = self.reference_counts
+            for layer_id in layer_ids:
+                if layer_id in rc:
+                    rc[layer_id] -= 1
+
     def prefetch_to_ram(self, layer_id: int):
         try:
             if self.layer_manager._prefetch_mode == "off":

@@ -28,6 +28,7 @@ class FitInMemoryPolicy(ComputePolicy):
 
     def configure_policy_for_model(self, req) -> None:
         self._mode = "fit"
+        self._run_arrays = {}            # tuple(run) -> ctypes int32 array handed to dn_shard_step
         local_count = max(1, len(self.runtime.assigned_layers))
         requested_w = max(1, int(req.window_size))
         self.window_size = min(local_count, requested_w)
@@ -53,7 +54,10 @@ class FitInMemoryPolicy(ComputePolicy):
         adv = 1 if run[-1] == rt._assigned_sorted[-1] else 0
         if rt.use_megakernel:
             # one persistent cooperative kernel for the whole step (dn_megakernel.cuh)
-            arr = (C.c_int32 * len(run))(*run)
+            key = tuple(run)
+            arr = self._run_arrays.get(key)
+            if arr is None:
+                arr = self._run_arrays[key] = (C.c_int32 * len(run))(*run)
             _cabi.check(lib.dn_shard_step(rt.model._h, arr, len(run), x.data_ptr(), ns.kv._h, int(is_tokens),
                                           int(fused_head), ns.result_token_ptr if fused_head else None,
                                           ns.result_logprob_ptr if fused_head else None, None, adv, s))
@@ -138,12 +142,11 @@ class FitInMemoryPolicy(ComputePolicy):
                             return
                         x = staged[0]
                     self._graph_step(ns, x, is_tokens, run, is_end and greedy)
-                    for lid in run:
-                        self.weight_cache.decrease_reference(lid)
+                    self.weight_cache.decrease_references(run)
                     if is_end and greedy:
                         rt.compute_stream.synchronize()
-                        final = TokenResult(token_id=int(ns.result_i32[0].item()),
-                                            logprob=float(ns.result_f32[1].item()) if msg.req_logprobs else 0.0,
+                        final = TokenResult(token_id=int(ns.result_np_i32[0]),
+                                            logprob=float(ns.result_np_f32[1]) if msg.req_logprobs else 0.0,
                                             top_logprobs={})
                 else:
                     staged = cc.stage_input(rt, msg, ns)

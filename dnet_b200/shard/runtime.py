@@ -60,6 +60,8 @@ class NonceState:
         res = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.result_i32 = res
         self.result_f32 = res.view(torch.float32)
+        self.result_np_i32 = res.numpy()                      # same pinned words, read without tensor indexing overhead
+        self.result_np_f32 = self.result_np_i32.view("float32")
         self.result_token_ptr = res.data_ptr()
         self.result_logprob_ptr = res.data_ptr() + 4
         self.x1 = torch.empty(1, model.hidden_size, dtype=torch.bfloat16, device="cuda")  # stable graph address
