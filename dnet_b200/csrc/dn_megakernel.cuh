@@ -3,21 +3,24 @@
 // Why: ncu on the per-op kernels (profiles/r01_*) shows every weight-streaming kernel moves
 // exactly its algorithmic bytes but is latency bound (59% long-scoreboard stalls, 16 warps/SM)
 // and pays ~10-14 us of launch + prologue + ramp + tail per launch, 160 launches per token.
-// This kernel removes both:
-//   * one CTA per SM (grid = #SMs), 9 warps: warp 8 is a PRODUCER that streams this CTA's
-//     share of every weight matrix of every layer through a shared-memory ring with TMA bulk
-//     copies (cp.async.bulk + mbarrier complete_tx): no registers are tied up by loads in
-//     flight, ~6 x 32 KB per SM are always outstanding, and because weights are immutable the
-//     producer never waits for a phase boundary -- HBM streams continuously across all the
-//     phases and layers of the step;
-//   * warps 0-7 are CONSUMERS: they wait on a stage's full-barrier, read the 16-row x 1024-col
-//     bf16 tile from shared memory (each warp owns 2 rows of the tile, so there is no
-//     cross-warp reduction and no block barrier per row block), keep fp32 partial sums, and
-//     run the same fused epilogues as the per-op kernels (RoPE + paged-KV append, residual,
-//     SwiGLU, argmax/logsumexp);
-//   * phases that depend on activations produced by other CTAs are separated by a grid
-//     barrier among consumer warps only (sense-reversing, bounded spin so a bug can never
-//     hang the GPU); five per layer.
+// This kernel removes both (DESIGN.md section 3.2 has the measured history):
+//   * one CTA per SM (grid = #SMs, cooperative launch), 12 warps = 3 warpgroups.
+//   * warps 8-9 are PRODUCERS: they stream this CTA's share of every weight matrix of every layer
+//     (and the lm_head) through a shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx, 16 rows x 1024 columns per stage).  No registers are tied up by loads in flight,
+//     and because weights are immutable the producers never wait for a phase boundary; they only
+//     bound the bytes outstanding (2-3 stages), because a deeper queue delays every barrier poll.
+//   * warps 0-7 are CONSUMERS: they wait on a stage's full-barrier and feed their 128-column slice
+//     of the 16 rows to the tensor cores (ldmatrix + mma.sync m16n8k16, activation replicated over
+//     the n columns, fp32 accumulate), merge the 8 slices per row block in fixed order and run the
+//     same fused epilogues as the per-op kernels (RoPE + paged-KV append, residual, SwiGLU,
+//     argmax/logsumexp).  setmaxnreg gives them 224 registers, the data-movement warpgroup 56.
+//   * phases that depend on activations produced by other CTAs are separated by a grid barrier
+//     (monotonic counter, release-arrive, a poller warp acquire-polls; bounded spins so a bug can
+//     never hang the GPU); five per layer.  While they wait the consumers keep draining the ring
+//     into TENSOR MEMORY (tcgen05.st, 8 stages per warp) and read the fragments back afterwards,
+//     so HBM streams through the barriers.
+//   * attention: one CTA per (q head, split), K/V rows global -> registers, fp32 online softmax.
 // Rounding points and summation structure per output row are fixed -> deterministic.
 #pragma once
 #include "dn_kernels.cuh"
@@ -27,13 +30,13 @@ namespace dn {
 constexpr int MK_CW = 8;                        // consumer warps
 constexpr int MK_CTHREADS = MK_CW * 32;         // 256
 constexpr int MK_PW = 2;                        // producer warps (alternate ring stages)
-constexpr int MK_THREADS = MK_CTHREADS + 4 * 32;   // + one warpgroup: 2 producers, the L2 prefetch warp, 1 idle warp
+constexpr int MK_THREADS = MK_CTHREADS + 4 * 32;   // + one warpgroup: 2 producers, the L2 prefetch warp, the barrier poller
 // register re-allocation (setmaxnreg works per warpgroup): the data-movement warpgroup gives most
 // of its registers to the 8 consumer warps.  8*32*224 + 4*32*56 = 64512 = 168*384
 constexpr int MK_REGS_CONSUMER = 224, MK_REGS_PRODUCER = 56;
 // the pool is what the CTA got at launch (168 regs x 384 threads), NOT the whole file: asking for more blocks forever
 static_assert(8 * 32 * MK_REGS_CONSUMER + 4 * 32 * MK_REGS_PRODUCER <= 168 * MK_THREADS, "setmaxnreg split exceeds the CTA's launch allocation");
-constexpr int MK_ROWS = 16;                     // rows per ring stage (two per consumer warp)
+constexpr int MK_ROWS = 16;                     // rows per ring stage = the M of one mma tile
 constexpr int MK_MAX_SEG = 1024;                // bf16 columns per row per stage: one 2 KiB TMA op per row
 // rows sit 16 bytes further apart than their payload, so the 8 row addresses of an ldmatrix fall
 // into 8 different bank groups (a 2 KiB pitch would put them all on the same 4 banks)
