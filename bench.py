@@ -476,6 +476,8 @@ def main():
     ap.add_argument("--fused-hop", type=int, default=1, help="N>1: wait+step+hop in one kernel")
     ap.add_argument("--pf-depth", type=int, default=-1, help="megakernel L2 prefetch look-ahead (ring stages); -1 = library default")
     ap.add_argument("--in-flight", type=int, default=0, help="sequences in flight at N>1 (default N)")
+    ap.add_argument("--split", default="balanced", choices=["balanced", "equal"],
+                    help="N>1: contiguous layer split balanced by streamed bytes (lm_head counted) or equal layer counts")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

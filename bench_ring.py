@@ -28,7 +28,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     from dnet_b200 import _cabi
     from dnet_b200.core.types.messages import ActivationMessage
     from dnet_b200.shard.models import ShardLoadModelRequest
-    from dnet_b200.shard.ring import HopReceiver, HopSender, device_view, even_split
+    from dnet_b200.shard.ring import HopReceiver, HopSender, balanced_split, device_view, even_split
     from dnet_b200.shard.runtime import ShardRuntime
     from dnet_b200.utils.model import SyntheticSource
     from tests.helpers import token_message
@@ -44,7 +44,13 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     L, H = cfg["num_hidden_layers"], cfg["hidden_size"]
     K, W = args.steps, args.warmup
     NS = world if args.in_flight <= 0 else args.in_flight
-    split = even_split(L, world)
+    if args.split == "equal":
+        split = even_split(L, world)
+    else:
+        # contiguous slices balanced by the bytes a shard streams per token (the last shard also owns the
+        # lm_head = 2.4 layers' worth): the assignment an operator posts to /v1/prepare_topology_manual
+        split = balanced_split(L, world, layer_bytes(cfg), first_extra=2 * cfg["hidden_size"],
+                               last_extra=2 * cfg["vocab_size"] * cfg["hidden_size"] + 2 * cfg["hidden_size"])
     mine = split[rank]
     first, last = rank == 0, rank == world - 1
     need = PROMPT_LEN + 2 * (W + K) + 96
@@ -370,7 +376,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
             "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"Llama-3-8B bf16 bs=1 decode, {world} shards x {len(mine)} layers pipelined ring "
+            "config": {"workload": f"Llama-3-8B bf16 bs=1 decode, {world} shards x {'/'.join(str(len(x)) for x in split)} layers ({args.split} contiguous split) pipelined ring "
                                    f"(BASELINE configs[1]), {NS} sequences in flight (one per shard), each bs=1",
                        "prompt_len": PROMPT_LEN, "kv": "fp16 paged (64-token pages)", "wire_dtype": "bf16",
                        "l2": "inputs larger than L2 (>=1.7 GB of weights per shard step vs 126 MB L2); no flush",

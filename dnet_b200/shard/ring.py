@@ -129,3 +129,35 @@ def even_split(num_layers: int, world: int) -> List[List[int]]:
         out.append(list(range(s, s + n)))
         s += n
     return out
+
+
+def balanced_split(num_layers: int, world: int, layer_bytes: int, first_extra: int = 0, last_extra: int = 0) -> List[List[int]]:
+    """contiguous split, k=1, that minimises the bytes of the busiest shard: with several sequences in
+    flight the ring's throughput is set by the shard that streams the most weight bytes per token, and
+    the shard with the last layer also streams the lm_head (`last_extra`; Llama-3-8B: 1.05 GB = 2.4
+    layers).  Any contiguous `LayerAssignment` is executed unchanged; this is the assignment an operator
+    would post to /v1/prepare_topology_manual instead of equal counts.  Ties: smallest sum of squares."""
+    if world <= 0 or num_layers < world:
+        raise ValueError("need at least one layer per shard")
+    INF = (float("inf"), float("inf"))
+    # best[r][l] = (max bytes, sum of squares) for the first r shards covering layers [0, l)
+    best = [[INF] * (num_layers + 1) for _ in range(world + 1)]
+    cut = [[0] * (num_layers + 1) for _ in range(world + 1)]
+    best[0][0] = (0, 0)
+    for r in range(1, world + 1):
+        for l in range(r, num_layers - (world - r) + 1):
+            for k in range(r - 1, l):
+                prev = best[r - 1][k]
+                if prev == INF:
+                    continue
+                load = (l - k) * layer_bytes + (first_extra if r == 1 else 0) + (last_extra if r == world else 0)
+                cand = (max(prev[0], load), prev[1] + load * load)
+                if cand < best[r][l]:
+                    best[r][l] = cand
+                    cut[r][l] = k
+    out, l = [], num_layers
+    for r in range(world, 0, -1):
+        k = cut[r][l]
+        out.append(list(range(k, l)))
+        l = k
+    return out[::-1]

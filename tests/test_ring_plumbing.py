@@ -198,3 +198,18 @@ def test_even_split_and_hop_endpoint_shapes():
     assert even_split(32, 8) == [list(range(i * 4, i * 4 + 4)) for i in range(8)]
     assert [len(x) for x in even_split(32, 5)] == [7, 7, 6, 6, 6]
     assert sum(even_split(80, 2), []) == list(range(80))
+    from dnet_b200.shard.ring import balanced_split
+    lb, head = 436_224_000, 1_050_673_152 + 8_192                 # Llama-3-8B layer / lm_head + final norm
+    for world in (1, 2, 4, 8):
+        sp = balanced_split(32, world, lb, first_extra=8_192, last_extra=head)
+        assert sum(sp, []) == list(range(32)) and all(len(x) >= 1 for x in sp)
+        loads = [len(x) * lb + (8_192 if i == 0 else 0) + (head if i == world - 1 else 0) for i, x in enumerate(sp)]
+        eq = even_split(32, world)
+        eq_loads = [len(x) * lb + (8_192 if i == 0 else 0) + (head if i == world - 1 else 0) for i, x in enumerate(eq)]
+        assert max(loads) <= max(eq_loads)
+    s8 = balanced_split(32, 8, lb, 8_192, head)
+    assert sorted(len(x) for x in s8[:-1]) == [4, 4, 4, 4, 4, 5, 5] and len(s8[-1]) == 2      # busiest shard: 5 layers, not 4 + head
+    assert [len(x) for x in balanced_split(32, 2, lb, 8_192, head)] == [17, 15]
+    assert [len(x) for x in balanced_split(6, 3, 10)] == [2, 2, 2]
+    with pytest.raises(ValueError):
+        balanced_split(2, 3, 10)
