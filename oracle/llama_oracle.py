@@ -129,6 +129,61 @@ class OracleKV:
         return self.k, self.v
 
 
+def mlx_affine_quantize(w: torch.Tensor, bits: int, group_size: int = 64):
+    """Restatement of mlx.core.quantize (affine mode) along the last axis, as used by
+    mlx_lm.models.cache.QuantizedKVCache (reference utils/model.py:505-554 selects it for
+    kv_bits 4/8).  Restated from the published algorithm, NOT verifiable in this tree (mlx is not
+    vendored): PARITY UNPINNED.  N4 groundwork -- the product does not build quantised KV yet.
+        per group: edge = the bound with the larger magnitude; scale = (max - min) / (2^bits - 1),
+        signed so that edge / scale >= 0, then snapped so that edge is exactly representable
+        (scale = edge / round(edge / scale)); bias = edge (0 when round(edge / scale) == 0);
+        code = clip(round((w - bias) / scale), 0, 2^bits - 1).
+    Returns (codes uint8 [..., n], scales [..., n/group], biases [..., n/group]) with scales / biases in
+    w.dtype; dequantised value = scale * code + bias."""
+    n_bins = float((1 << bits) - 1)
+    shape = w.shape
+    g = w.to(torch.float32).reshape(*shape[:-1], shape[-1] // group_size, group_size)
+    w_max, w_min = g.amax(-1, keepdim=True), g.amin(-1, keepdim=True)
+    mask = w_min.abs() > w_max.abs()
+    scales = torch.clamp((w_max - w_min) / n_bins, min=1e-7)
+    scales = torch.where(mask, scales, -scales)
+    edge = torch.where(mask, w_min, w_max)
+    q0 = torch.round(edge / scales)
+    scales = torch.where(q0 != 0, edge / q0, scales)
+    biases = torch.where(q0 == 0, torch.zeros_like(edge), edge)
+    scales, biases = scales.to(w.dtype), biases.to(w.dtype)             # stored in the cache dtype
+    codes = torch.clamp(torch.round((g - biases.to(torch.float32)) / scales.to(torch.float32)), 0, n_bins).to(torch.uint8)
+    return codes.reshape(shape), scales.squeeze(-1), biases.squeeze(-1)
+
+
+def mlx_affine_dequantize(codes: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64) -> torch.Tensor:
+    shape = codes.shape
+    g = codes.to(torch.float32).reshape(*shape[:-1], shape[-1] // group_size, group_size)
+    return (g * scales.to(torch.float32).unsqueeze(-1) + biases.to(torch.float32).unsqueeze(-1)).reshape(shape)
+
+
+class OracleQuantKV(OracleKV):
+    """QuantizedKVCache semantics: every appended K / V row is quantised per group of 64 along
+    head_dim and attention runs on the dequantised values (mlx_lm quantized SDPA computes
+    q.(s*c+b) and p.(s*c+b) with fp32 accumulation)."""
+
+    def __init__(self, bits: int, group_size: int = 64) -> None:
+        super().__init__()
+        self.bits, self.group_size = int(bits), int(group_size)
+        self._parts: List[Tuple[torch.Tensor, ...]] = []
+
+    def update_and_fetch(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        kq = mlx_affine_quantize(k, self.bits, self.group_size)
+        vq = mlx_affine_quantize(v, self.bits, self.group_size)
+        self._parts.append((kq, vq))
+        kd = mlx_affine_dequantize(*kq, self.group_size)
+        vd = mlx_affine_dequantize(*vq, self.group_size)
+        self.k = kd if self.k is None else torch.cat([self.k, kd], dim=1)     # fp32 dequantised view
+        self.v = vd if self.v is None else torch.cat([self.v, vd], dim=1)
+        self.offset = self.k.shape[1]
+        return self.k, self.v
+
+
 class LlamaOracle:
     """Restates BaseRingModel's operator API (reference core/models/base.py:20-73)
     on torch-CPU.  ``dtype`` is the storage dtype T (bfloat16 for the parity

@@ -108,3 +108,54 @@ def test_oracle_shard_routes_like_fit_policy():
     assert kind == "activation" and last == 1 and x.shape == (len(g["prompt"]), cfg.hidden_size)
     with pytest.raises(RuntimeError):
         sh.process("n", x, "bfloat16", 2)       # layer 3 is not hosted here
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_affine_kv_quantiser_properties(bits):
+    """N4 groundwork (restated mx.quantize, parity unpinned): codes in range, the large-magnitude bound of
+    every group is reproduced exactly (up to the bf16 storage of scale / bias), error within one step (the
+    snapped scale can leave the far bound just outside the code range, where it clips), constant groups
+    survive, 8 bits beat 4 bits."""
+    from oracle.llama_oracle import mlx_affine_dequantize, mlx_affine_quantize
+    g = torch.Generator().manual_seed(bits)
+    w = (torch.randn(3, 5, 128, generator=g) * 0.7).to(torch.bfloat16)
+    w[0, 0, :64] = 0.25                                            # constant group
+    codes, sc, bi = mlx_affine_quantize(w, bits)
+    assert codes.dtype == torch.uint8 and int(codes.max()) <= (1 << bits) - 1
+    assert sc.shape == (3, 5, 2) and bi.shape == (3, 5, 2) and sc.dtype == torch.bfloat16
+    d = mlx_affine_dequantize(codes, sc, bi)
+    err = (d - w.float()).abs().reshape(3, 5, 2, 64)
+    bound = sc.float().abs().unsqueeze(-1) * 1.0 + 2.0 ** -7 * w.float().abs().amax() + 1e-6
+    assert bool((err <= bound).all())
+    assert float(err[0, 0, 0].max()) <= 2.0 ** -8 * 0.25 + 1e-6
+    if bits == 8:
+        c4, s4, b4 = mlx_affine_quantize(w, 4)
+        assert (mlx_affine_dequantize(c4, s4, b4) - w.float()).abs().mean() > err.mean()
+
+
+def test_quantised_kv_cache_tracks_the_float_cache():
+    """The oracle with an 8-bit KV cache stays close to the bf16-cache oracle, 4-bit is further away,
+    offsets advance identically (mlx_lm QuantizedKVCache semantics)."""
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV, OracleQuantKV, make_weights
+    cfg = OracleConfig.from_dict(dict(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, head_dim=128, intermediate_size=512,
+                                      vocab_size=97, num_hidden_layers=2, rms_norm_eps=1e-5, rope_theta=10000.0, model_type="llama",
+                                      tie_word_embeddings=False))
+    w = make_weights(cfg, 11)
+    orc = LlamaOracle(cfg, w)
+    ids = torch.tensor([5, 17, 3, 88, 41, 2, 9], dtype=torch.int32)
+
+    def run(mk):
+        kv = {l: mk() for l in range(2)}
+        x = orc.embed(ids)
+        for l in range(2):
+            x = orc.apply_single_layer(l, x, kv[l])
+        x2 = orc.embed(torch.tensor([7], dtype=torch.int32))
+        for l in range(2):
+            x2 = orc.apply_single_layer(l, x2, kv[l])
+        assert kv[0].offset == 8
+        return orc.lm_project(orc.normalize(x2), return_fp32=True)[0]
+
+    ref = run(OracleKV)
+    e8 = float((run(lambda: OracleQuantKV(8)) - ref).abs().max() / ref.abs().max())
+    e4 = float((run(lambda: OracleQuantKV(4)) - ref).abs().max() / ref.abs().max())
+    assert e8 < 0.05 and e8 < e4
