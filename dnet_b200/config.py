@@ -45,6 +45,12 @@ class TransportSettings:  # reference config.py:108-127 (prefix DNET_TRANSPORT_)
     wire_dtype: str = field(default_factory=lambda: _env("DNET_TRANSPORT_WIRE_DTYPE", "fp16"))
     streaming: bool = True
     stream_idle_s: float = 2.0
+    stream_backoff_s: float = 0.5
+    # device-hop transport (dnet_b200): lanes = nonces in flight per ring, bulk slot = one prefill chunk
+    hop_lanes: int = field(default_factory=lambda: _env("DNET_TRANSPORT_HOP_LANES", 16, int))
+    hop_bulk_tokens: int = field(default_factory=lambda: _env("DNET_TRANSPORT_HOP_BULK_TOKENS", 512, int))
+    sched_rounds_per_frame: int = field(default_factory=lambda: _env("DNET_TRANSPORT_SCHED_ROUNDS", 4, int))
+    sched_frames_in_flight: int = field(default_factory=lambda: _env("DNET_TRANSPORT_SCHED_DEPTH", 3, int))
     compress: bool = False
     compress_min_bytes: int = 65536
 

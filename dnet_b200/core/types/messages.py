@@ -40,6 +40,13 @@ class ActivationMessage:
     # dnet_b200 extension: torch.cuda.Event recorded after the kernels that produce ``tensor``
     # were enqueued; a consumer on another stream orders itself after it (device hand-off)
     ready_event: Optional[Any] = None
+    # dnet_b200 device-hop transport (shard/frames.py, shard/adapters/ring.py):
+    lane: int = -1                       # hop lane of the nonce (same index on every shard), -1 = none
+    seq0: int = 0                        # decode-flag value the request's first on-device decode step waits for
+    hop_wait: Optional[Tuple[int, int, int]] = None   # (arrival flag ptr, seq, consumed flag ptr): tensor is a hop slot
+    sched: Optional[Any] = None          # b200.sched: ordered [(lane, seq)] decode entries
+    sched_done: Optional[Any] = None     # SchedTicket: lets the head's scheduler bound the frames in flight
+    hop_meta: Optional[Any] = None       # set by the egress hook once the tensor went out over NVLink
 
     @classmethod
     def from_proto(cls, proto_msg, pool_id: int = 0):

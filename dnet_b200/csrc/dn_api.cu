@@ -947,6 +947,13 @@ extern "C" int dn_step_error(dn_model* m, dn_stream s) {
   return (int)v;
 }
 
+// the error word is sticky (every later step reports it): clear it once the failed request was dropped
+extern "C" int dn_step_error_clear(dn_model* m, dn_stream s) {
+  if (!m) return fail(DN_EINVAL, "null model");
+  CK(cudaMemsetAsync(m->mk_sync + 2, 0, 4, (cudaStream_t)s));
+  return DN_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // graphs
 // ---------------------------------------------------------------------------------

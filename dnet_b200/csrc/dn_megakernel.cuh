@@ -1085,11 +1085,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       if (lane == 0) {
         const float lse = bf16r(m + logf(l));
         const float lp = bf16r(__fsub_rn(m, lse));
-        if (p.token_out != nullptr) *p.token_out = idx;
-        if (p.logprob_out != nullptr) *p.logprob_out = lp;
+        // host-visible result (token_out / logprob_out may be pinned host memory polled WITHOUT a stream sync,
+        // shard/token_tap.py): logprob first, system fence, then the token.  A timed-out bounded wait makes the
+        // step's results invalid: the host then sees -(1000 + code) instead of a token id.
+        const unsigned int ecode = *reinterpret_cast<volatile unsigned int*>(p.err);
+        if (p.logprob_out != nullptr) *reinterpret_cast<volatile float*>(p.logprob_out) = lp;
         p.st->token = idx;
         *p.head_ticket = 0u;
         if (p.send_dst != nullptr) *reinterpret_cast<volatile int32_t*>(p.send_dst) = idx;   // token hop to shard 0
+        __threadfence_system();
+        if (p.token_out != nullptr) *reinterpret_cast<volatile int32_t*>(p.token_out) = ecode ? -(1000 + (int)ecode) : idx;
         __threadfence_system();
         if (p.send_flag != nullptr)
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.send_flag), "r"(p.send_seq) : "memory");

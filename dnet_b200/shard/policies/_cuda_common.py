@@ -39,20 +39,61 @@ def local_run(rt, current_layer: int) -> List[int]:
     return run
 
 
+def note_lane(rt, msg: ActivationMessage, ns) -> None:
+    """Remember which hop lane the nonce rides (device-hop transport; set by the adapter's ingress)."""
+    if msg.lane >= 0 and ns.lane != msg.lane:
+        ns.lane = msg.lane
+        rt.lane_nonce[msg.lane] = msg.nonce
+    if msg.lane >= 0:
+        ns.params = {"callback_url": msg.callback_url, "logprobs": bool(msg.req_logprobs), "seq0": msg.seq0}
+
+
+def _input_copy_event(rt):
+    """Event behind the cudaMemcpyAsync that reads a pinned input-pool buffer: the buffer is released
+    (and may be refilled by codec.deserialize for another request) only after the copy has run."""
+    import ctypes as C
+
+    lib = _cabi.load()
+    ev = C.c_void_p()
+    _cabi.check(lib.dn_event_create(C.byref(ev), 0))
+    _cabi.check(lib.dn_event_record(ev.value, rt.compute_stream_ptr))
+    return ev.value
+
+
+def finish_input(rt, msg: ActivationMessage, ns) -> None:
+    """Release the message's input buffer -- deferred behind its H2D copy when one is queued."""
+    ev = getattr(ns, "input_copy_event", None) if ns is not None else None
+    if ns is not None:
+        ns.input_copy_event = None
+    rt.release_input(msg.pool_id, ev)
+
+
 def stage_input(rt, msg: ActivationMessage, ns) -> Optional[Tuple[torch.Tensor, int, bool]]:
     """Returns (x [T,H] bf16 device view of the nonce's activation buffer, T, is_tokens).
 
     tokens : pinned int32 ids -> HBM (cudaMemcpyAsync) -> embed kernel -> cast to wire dtype
-    tensor : device tensor handed over by the NVLink hop (msg.tensor) or pinned wire bytes
-             from the pool -> HBM
+    tensor : device tensor handed over by the NVLink hop (msg.tensor; with ``hop_wait`` it is this
+             shard's own bulk slot and the stream first waits for the sender's sequence flag) or
+             pinned wire bytes from the pool -> HBM
     """
     lib = _cabi.load()
     s = rt.compute_stream_ptr
     model = rt.model
     H = model.hidden_size
+    ns.input_copy_event = None
+    if ns.hop_sent_event is not None:      # the previous result of this nonce may still be leaving over NVLink
+        rt.compute_stream.wait_event(ns.hop_sent_event)
+        ns.hop_sent_event = None
     if msg.tensor is not None and msg.dtype != "tokens":
         src = msg.tensor.reshape(-1, H)
         T = src.shape[0]
+        if msg.hop_wait is not None:
+            flag, seq, consumed = msg.hop_wait
+            err = rt.hop.rx_bulk.err_flag if rt.hop is not None else None
+            _cabi.check(lib.dn_hop_wait(flag, seq, 20000, err, s))
+            x = ns.x_view(T)
+            _cabi.check(lib.dn_hop_send(x.data_ptr(), src.data_ptr(), T * H * 2, consumed, seq, s))   # copy out + credit
+            return x, T, False
         if msg.ready_event is not None:
             rt.compute_stream.wait_event(msg.ready_event)
         else:   # unknown producer stream: order after everything enqueued on the current stream
@@ -80,6 +121,7 @@ def stage_input(rt, msg: ActivationMessage, ns) -> Optional[Tuple[torch.Tensor, 
                 src = src.to(torch.int32)
             _cabi.check(lib.dn_memcpy_h2d(ids_dev.data_ptr(), src.data_ptr(), T * 4, s))
             ns.keepalive = src
+            ns.input_copy_event = _input_copy_event(rt)
             ids_ptr = ids_dev.data_ptr()
         x = ns.x_view(T)
         _cabi.check(lib.dn_embed(model._h, ids_ptr, T, x.data_ptr(), s))
@@ -92,6 +134,7 @@ def stage_input(rt, msg: ActivationMessage, ns) -> Optional[Tuple[torch.Tensor, 
     src = input_buffer[:input_size]
     _cabi.check(lib.dn_memcpy_h2d(x.data_ptr(), src.data_ptr(), input_size * 2, s))
     ns.keepalive = src
+    ns.input_copy_event = _input_copy_event(rt)
     return x, T, False
 
 
@@ -120,7 +163,7 @@ def build_output(rt, msg: ActivationMessage, x: torch.Tensor, last_layer: int, f
     shape = (1, int(x.shape[0]), int(x.shape[1]))
     common = dict(nonce=msg.nonce, layer_id=last_layer, pool_id=-1, shape=shape, batch_size=msg.batch_size,
                   timestamp=utc_epoch_now(), node_origin=f"shard_{rt.shard_id}", dtype=rt._wire_dtype_str,
-                  callback_url=msg.callback_url)
+                  callback_url=msg.callback_url, lane=msg.lane, seq0=msg.seq0)
     if final is not None:
         return ActivationMessage(**common, is_final=True, token_id=final.token_id, logprob=final.logprob,
                                  top_logprobs=final.top_logprobs)

@@ -18,6 +18,7 @@ from dnet_b200 import _cabi
 from dnet_b200.core.memory.weight_cache import WeightCache
 from dnet_b200.core.types.messages import ActivationMessage, TokenResult
 from dnet_b200.utils.logger import logger
+from .. import frames as fr
 from . import _cuda_common as cc
 from .base import ComputePolicy, register_policy
 
@@ -87,8 +88,99 @@ class FitInMemoryPolicy(ComputePolicy):
         if adv:
             ns.kv.note_advance(1)
 
-    def process(self, msg: ActivationMessage) -> None:
+    # -- device-closed decode: one fused wait + step + hop kernel per scheduled (lane, seq) -----
+    def _process_sched(self, msg: ActivationMessage) -> None:
+        """A ``b200.sched`` frame (shard/frames.py): the head shard's ordered decode schedule.  Every shard
+        launches the entries in exactly this order on its one compute stream, so kernels that spin on a
+        predecessor's flag can never wait behind a kernel that (transitively) waits for them.
+        Per entry: wait for flag ``seq`` of the lane (the token on the head shard, the activation
+        elsewhere), run this shard's layers (in place in the lane slot), store the result into the
+        successor's slot and release its flag -- all inside ``dn_shard_step_hop``; the finalising shard
+        hands the token to the head's slot with ``seq + 1`` and to the host through the TokenTap."""
         rt = self.runtime
+        hop = rt.hop
+        ticket = msg.sched_done
+        try:
+            with rt._model_lock:
+                if not cc.model_ready(rt) or hop is None or not hop.connected:
+                    logger.error("Runtime %s: schedule frame without a model / hop link", rt.shard_id)
+                    return
+                lib = _cabi.load()
+                run = list(rt._assigned_sorted)
+                if run != list(range(run[0], run[0] + len(run))):
+                    logger.error("on-device decode needs one contiguous run of local layers (k=1); got %s", run)
+                    return
+                first = run[0] == 0
+                last = run[-1] + 1 >= rt.model_metadata.num_layers
+                to_bind = self._bind_layer_weights(run, msg)
+                if to_bind is None:
+                    return
+                if to_bind:
+                    cc.wait_layers_ready(rt, self.weight_cache, run)
+                    rt.model.load_weights(list(to_bind.items()), strict=False)
+                key = tuple(run)
+                arr = self._run_arrays.get(key)
+                if arr is None:
+                    arr = self._run_arrays[key] = (C.c_int32 * len(run))(*run)
+                s = rt.compute_stream_ptr
+                now = None
+                for lane, seq in msg.sched:
+                    nonce = rt.lane_nonce.get(lane)
+                    ns = rt._kv_by_nonce.get(nonce) if nonce is not None else None
+                    if ns is None:
+                        logger.error("schedule entry for lane %d: no request holds that lane on shard %s", lane, rt.shard_id)
+                        continue
+                    tok_ptr = lp_ptr = None
+                    if last:
+                        tok_ptr, lp_ptr = rt.token_tap.post(lane, (nonce, seq, ns.params))
+                    _cabi.check(lib.dn_shard_step_hop(
+                        rt.model._h, arr, len(run), ns.x1.data_ptr() if first else hop.rx.slot(lane), ns.kv._h,
+                        1 if first else 0, 1 if last else 0, tok_ptr, lp_ptr, 1,
+                        hop.rx.flag(lane), seq, hop.rx.slot(lane) if first else None,
+                        hop.tx_slot(lane), hop.tx_flag(lane), seq + 1 if last else seq, s))
+                    if now is None:
+                        import time
+                        now = time.perf_counter()
+                    rt._kv_last_seen[nonce] = now
+                if not (len(rt._assigned_sorted) <= self.window_size):
+                    self.weight_cache.decrease_references(run)
+        except Exception as e:
+            logger.exception("Error launching scheduled decode steps: %s", e)
+        finally:
+            if ticket is not None:
+                ev = None
+                try:
+                    import torch
+                    ev = torch.cuda.Event()
+                    ev.record(rt.compute_stream)
+                except Exception:
+                    ev = None
+                ticket.record(ev)
+
+    def _process_seed(self, msg: ActivationMessage) -> None:
+        """A seeded ``b200.lease``: put ``msg.token_id`` into the head shard's own lane slot and publish
+        the lane's next decode sequence number (used when a lease follows host-driven steps)."""
+        rt = self.runtime
+        try:
+            with rt._model_lock:
+                ns = rt._kv_by_nonce.get(msg.nonce)
+                if ns is None or rt.hop is None or msg.lane < 0:
+                    logger.error("seeded lease for unknown nonce %s", msg.nonce)
+                    return
+                lib = _cabi.load()
+                ns.kv.set_token(int(msg.token_id), rt.compute_stream_ptr)
+                _cabi.check(lib.dn_hop_send(rt.hop.rx.slot(msg.lane), ns.kv.token_ptr, 4, rt.hop.rx.flag(msg.lane),
+                                            msg.seq0, rt.compute_stream_ptr))
+        except Exception as e:
+            logger.exception("Error seeding lease: %s", e)
+
+    def process(self, msg: ActivationMessage) -> None:
+        if msg.dtype == fr.SCHED_DTYPE:
+            return self._process_sched(msg)
+        if msg.dtype == fr.LEASE_DTYPE:
+            return self._process_seed(msg)
+        rt = self.runtime
+        ns = None
         try:
             with rt._model_lock:
                 if not cc.model_ready(rt):
@@ -96,6 +188,7 @@ class FitInMemoryPolicy(ComputePolicy):
                     return
                 # 1) per-nonce KV (+ activation buffer, captured graphs, pinned result)
                 ns = rt.get_or_make_kv(msg.nonce)
+                cc.note_lane(rt, msg, ns)
                 T = cc.msg_tokens(rt, msg)
                 current_layer = msg.layer_id + 1
                 run = cc.local_run(rt, current_layer)
@@ -145,6 +238,14 @@ class FitInMemoryPolicy(ComputePolicy):
                     self.weight_cache.decrease_references(run)
                     if is_end and greedy:
                         rt.compute_stream.synchronize()
+                        if int(ns.result_np_i32[0]) <= -1000:
+                            # a bounded in-kernel wait timed out: the step's results are invalid (sticky until cleared)
+                            code = -int(ns.result_np_i32[0]) - 1000
+                            rt.step_errors += 1
+                            _cabi.load().dn_step_error_clear(rt.model._h, rt.compute_stream_ptr)
+                            logger.error("step kernel error %d for nonce %s: request failed, no token emitted", code, msg.nonce)
+                            cc.finish_input(rt, msg, ns)
+                            return
                         final = TokenResult(token_id=int(ns.result_np_i32[0]),
                                             logprob=float(ns.result_np_f32[1]) if msg.req_logprobs else 0.0,
                                             top_logprobs={})
@@ -170,13 +271,13 @@ class FitInMemoryPolicy(ComputePolicy):
                         return
                 output_msg = cc.build_output(rt, msg, x, last_layer, final)
                 rt.emit_result(output_msg)
-                rt.input_pool.release(msg.pool_id)
+                cc.finish_input(rt, msg, ns)
                 return
         except Exception as e:
             logger.exception("Error in fit policy process: %s", e)
             try:
                 if rt.input_pool:
-                    rt.input_pool.release(msg.pool_id)
+                    cc.finish_input(rt, msg, ns)
             except Exception:
                 pass
         finally:

@@ -21,6 +21,7 @@ from concurrent.futures import Future
 from dnet_b200.core.memory.weight_cache import WeightCache
 from dnet_b200.core.types.messages import ActivationMessage
 from dnet_b200.utils.logger import logger
+from .. import frames as fr
 from . import _cuda_common as cc
 from .base import ComputePolicy, register_policy
 
@@ -80,6 +81,13 @@ class OffloadPolicy(ComputePolicy):
 
     def process(self, msg: ActivationMessage) -> None:
         rt = self.runtime
+        if msg.dtype in (fr.SCHED_DTYPE, fr.LEASE_DTYPE):
+            # on-device decode leases need every layer resident (one persistent kernel per step); a shard that
+            # swaps layers serves decode through the per-message path and the API must drive tokens itself
+            logger.error("shard %s runs in %s mode: on-device decode schedules are not supported here", rt.shard_id, self._mode)
+            if msg.sched_done is not None:
+                msg.sched_done.record(None)
+            return
         if not cc.model_ready(rt):
             logger.error("Runtime %s: cannot process activation - model not loaded", rt.shard_id)
             return
@@ -89,6 +97,7 @@ class OffloadPolicy(ComputePolicy):
                     logger.error("Runtime %s: cannot process activation - model not loaded", rt.shard_id)
                     return
                 ns = rt.get_or_make_kv(msg.nonce)
+                cc.note_lane(rt, msg, ns)
                 T = cc.msg_tokens(rt, msg)
                 if T <= 0 or ns.kv.offset + T > ns.kv.max_tokens:
                     logger.error("bad message size / KV capacity exceeded for nonce %s", msg.nonce)
@@ -219,7 +228,7 @@ class OffloadPolicy(ComputePolicy):
                         return
                 output_msg = cc.build_output(rt, msg, x, last_layer, final)
                 rt.emit_result(output_msg)
-                rt.input_pool.release(msg.pool_id)
+                cc.finish_input(rt, msg, ns)
 
                 # schedule prefetch of the next local window, or wrap to the first window so the
                 # next token's first copies overlap the other shards' compute

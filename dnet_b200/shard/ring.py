@@ -51,14 +51,17 @@ class HopEndpoint:
 
 
 class HopReceiver:
-    """Receiver-owned slots: ``n_slots`` x ``slot_bytes`` of HBM + one uint32 flag each (+1 error flag)."""
+    """Receiver-owned slots: ``n_slots`` x ``slot_bytes`` of HBM, one uint32 *arrival* flag and one
+    *consumed* flag each (one 64-byte line per flag), + 1 error flag.  The consumed flag is written
+    by the receiver's compute stream once it has copied a bulk slot out; the sender polls it over
+    NVLink before overwriting the slot (credit for single-buffered prefill chunks)."""
 
     def __init__(self, n_slots: int, slot_bytes: int):
         self.lib = _cabi.load()
         self.n_slots, self.slot_bytes = n_slots, slot_bytes
         d, f = C.c_void_p(), C.c_void_p()
         _cabi.check(self.lib.dn_hop_alloc(n_slots * slot_bytes, C.byref(d)))
-        _cabi.check(self.lib.dn_hop_alloc((n_slots + 1) * 64, C.byref(f)))   # one 64-byte line per flag
+        _cabi.check(self.lib.dn_hop_alloc((2 * n_slots + 1) * 64, C.byref(f)))   # one 64-byte line per flag
         self.data_ptr, self.flag_ptr = d.value, f.value
 
     def slot(self, i: int) -> int:
@@ -67,9 +70,16 @@ class HopReceiver:
     def flag(self, i: int) -> int:
         return self.flag_ptr + i * 64
 
+    def consumed_flag(self, i: int) -> int:
+        return self.flag_ptr + (self.n_slots + i) * 64
+
     @property
     def err_flag(self) -> int:
-        return self.flag_ptr + self.n_slots * 64
+        return self.flag_ptr + 2 * self.n_slots * 64
+
+    def mark_consumed(self, i: int, seq: int, stream: int) -> None:
+        """publish on the compute stream that slot i's contents up to ``seq`` were copied out"""
+        _cabi.check(self.lib.dn_hop_send(self.slot(i), self.slot(i), 0, self.consumed_flag(i), seq, stream))
 
     def endpoint(self) -> HopEndpoint:
         hd, hf = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
@@ -113,10 +123,77 @@ class HopSender:
         _cabi.check(self.lib.dn_hop_send(self.data_ptr + i * self.ep.slot_bytes, src_ptr, nbytes,
                                          self.flag_ptr + i * 64, seq, stream))
 
+    def wait_consumed(self, i: int, seq: int, stream: int, timeout_ms: int = 20000) -> None:
+        """make ``stream`` wait until the peer has copied out everything up to ``seq`` from slot i"""
+        if seq <= 0:
+            return
+        _cabi.check(self.lib.dn_hop_wait(self.flag_ptr + (self.ep.n_slots + i) * 64, seq, timeout_ms, None, stream))
+
     def close(self) -> None:
         if self._imported:
             self.lib.dn_hop_close(self.data_ptr)
             self.lib.dn_hop_close(self.flag_ptr)
+
+
+class HopLink:
+    """One shard's device-hop state: its own receive lanes and the ring successor's lanes.
+
+    Per lane (= per in-flight nonce) the receiver owns a *decode* slot (one activation row, H bf16;
+    on the head shard its first 4 bytes double as the token slot) and a *bulk* slot (a prefill chunk of
+    up to ``bulk_tokens`` rows), each with its own 32-bit sequence flag.  ``endpoint()`` is what the
+    predecessor needs to map them (four CUDA IPC handles, picklable / hex-serialisable);
+    ``connect(endpoint)`` maps the successor's lanes.  In a single-shard ring the shard is its own
+    successor and no IPC is involved.
+    """
+
+    def __init__(self, n_lanes: int, hidden: int, bulk_tokens: int = 512):
+        self.n_lanes, self.hidden, self.bulk_tokens = int(n_lanes), int(hidden), int(bulk_tokens)
+        self.rx = HopReceiver(self.n_lanes, hidden * 2)
+        self.rx_bulk = HopReceiver(self.n_lanes, self.bulk_tokens * hidden * 2)
+        self.tx: Optional[HopSender] = None
+        self.tx_bulk: Optional[HopSender] = None
+
+    def endpoint(self) -> dict:
+        a, b = self.rx.endpoint(), self.rx_bulk.endpoint()
+        return {"n_lanes": self.n_lanes, "hidden": self.hidden, "bulk_tokens": self.bulk_tokens,
+                "decode": [a.data_handle.hex(), a.flag_handle.hex()], "bulk": [b.data_handle.hex(), b.flag_handle.hex()]}
+
+    def connect(self, ep: Optional[dict]) -> None:
+        """ep=None: self-loop (single shard, or a successor living in this process passes its HopLink)."""
+        if ep is None:
+            self.connect_local(self)
+            return
+        if ep["n_lanes"] != self.n_lanes or ep["hidden"] != self.hidden:
+            raise ValueError(f"hop endpoint mismatch: peer lanes/hidden {ep['n_lanes']}/{ep['hidden']} vs "
+                             f"{self.n_lanes}/{self.hidden}")
+        d = HopEndpoint(bytes.fromhex(ep["decode"][0]), bytes.fromhex(ep["decode"][1]), self.n_lanes, self.hidden * 2)
+        b = HopEndpoint(bytes.fromhex(ep["bulk"][0]), bytes.fromhex(ep["bulk"][1]), self.n_lanes,
+                        int(ep["bulk_tokens"]) * self.hidden * 2)
+        self.tx, self.tx_bulk = HopSender(d), HopSender(b)
+
+    def connect_local(self, peer: "HopLink") -> None:
+        d = HopEndpoint(b"", b"", peer.n_lanes, peer.hidden * 2)
+        b = HopEndpoint(b"", b"", peer.n_lanes, peer.bulk_tokens * peer.hidden * 2)
+        self.tx = HopSender(d, (peer.rx.data_ptr, peer.rx.flag_ptr))
+        self.tx_bulk = HopSender(b, (peer.rx_bulk.data_ptr, peer.rx_bulk.flag_ptr))
+
+    @property
+    def connected(self) -> bool:
+        return self.tx is not None
+
+    def tx_slot(self, lane: int) -> int:
+        return self.tx.data_ptr + lane * self.tx.ep.slot_bytes
+
+    def tx_flag(self, lane: int) -> int:
+        return self.tx.flag_ptr + lane * 64
+
+    def close(self) -> None:
+        for t in (self.tx, self.tx_bulk):
+            if t is not None:
+                t.close()
+        self.tx = self.tx_bulk = None
+        self.rx.free()
+        self.rx_bulk.free()
 
 
 def even_split(num_layers: int, world: int) -> List[List[int]]:

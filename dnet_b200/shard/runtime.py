@@ -57,6 +57,10 @@ class NonceState:
         self._ids: Optional[torch.Tensor] = None
         self.graphs: Dict[Any, int] = {}
         self.keepalive = None
+        self.lane: int = -1                       # hop lane of the nonce (device-hop transport), -1 = none
+        self.params: Dict[str, Any] = {}          # request parameters the token tap needs (callback url, logprobs)
+        self.hop_sent_event = None                # comm-stream event: the activation buffer's last hop copy has run
+        self.input_copy_event = None              # event behind the H2D copy out of the pinned input buffer
         res = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.result_i32 = res
         self.result_f32 = res.view(torch.float32)
@@ -110,7 +114,10 @@ class ShardRuntime:
         self.activation_send_queue: Queue[ActivationMessage] = Queue(maxsize=queue_size)
         self.compute_thread: Optional[threading.Thread] = None
         self.running = False
-        self.executor = ThreadPoolExecutor(max_workers=int(self._device_prefetch_workers or 4))
+        # CUDA device of this shard = the creating thread's current device; worker threads bind to it
+        self._device_index: Optional[int] = int(torch.cuda.current_device()) if torch.cuda.is_available() else None
+        self.executor = ThreadPoolExecutor(max_workers=int(self._device_prefetch_workers or 4),
+                                           initializer=self._bind_thread_device)
         self.assigned_layers: List[int] = []
         self._assigned_sorted: List[int] = []
         self._assigned_set: set = set()
@@ -137,6 +144,15 @@ class ShardRuntime:
         self.use_megakernel: bool = bool(self._compute_settings.megakernel)
         self.stage_host: bool = True
         self._api_tensors: Dict[str, torch.Tensor] = {}
+        # device-hop transport state, owned by the topology adapter (shard/adapters/ring.py)
+        self.comm_stream: Optional[torch.cuda.Stream] = None   # second stream: ring hops overlap the next nonce's compute
+        self.hop = None                      # HopLink: this shard's receive lanes + the successor's
+        self.hop_pending = None              # HopLink being set up (answers the predecessor's endpoint request)
+        self.on_emit = None                  # adapter hook run by emit_result on the compute thread
+        self.token_tap = None                # TokenTap on the finalising shard
+        self.lane_nonce: Dict[int, str] = {}
+        self._deferred_releases: List[Any] = []   # (pool_id, event) input buffers whose H2D copy is still queued
+        self.step_errors = 0
 
     @property
     def compute_config(self):
@@ -156,8 +172,58 @@ class ShardRuntime:
     def queue_size(self) -> int:
         return self.activation_recv_queue.qsize()
 
+    # -- C ABI shorthands used by the adapter hook --------------------------------------------
+    @property
+    def lib(self):
+        return _cabi.load()
+
+    @staticmethod
+    def check(rc: int) -> int:
+        return _cabi.check(rc)
+
+    def _bind_thread_device(self) -> None:
+        """The CUDA current device is per thread and defaults to 0: every worker thread (compute,
+        executor / prefetch) binds to the shard's device before touching CUDA."""
+        dev = self._device_index
+        if dev is not None and torch.cuda.is_available():
+            torch.cuda.set_device(dev)
+
     def emit_result(self, msg: ActivationMessage) -> None:
+        hook = self.on_emit
+        if hook is not None:
+            try:
+                hook(msg)      # device hop of the tensor / first token, before the frame is queued
+            except Exception as e:
+                logger.error("egress hook failed for nonce %s (%s); the frame falls back to bytes", msg.nonce, e)
         self.activation_send_queue.put_nowait(msg)
+
+    # -- input buffers whose host->device copy is still queued ------------------------------------
+    def release_input(self, pool_id: int, event=None) -> None:
+        """input_pool.release that respects an in-flight cudaMemcpyAsync out of the pinned buffer: with an
+        event the buffer only becomes FREE (reusable by codec.deserialize) once the copy has run."""
+        if self.input_pool is None or pool_id is None or pool_id < 0:
+            return
+        if event is not None:
+            self._deferred_releases.append((pool_id, event))
+        else:
+            self.input_pool.release(pool_id)
+        self.reap_releases()
+
+    def reap_releases(self, wait: bool = False) -> None:
+        if not self._deferred_releases:
+            return
+        lib = _cabi.load()
+        keep = []
+        for pid, ev in self._deferred_releases:
+            if wait:
+                lib.dn_event_sync(ev)
+            if wait or lib.dn_event_query(ev) == 1:
+                lib.dn_event_destroy(ev)
+                if self.input_pool is not None:
+                    self.input_pool.release(pid)
+            else:
+                keep.append((pid, ev))
+        self._deferred_releases = keep
 
     def all_nonce_states(self):
         return list(self._kv_by_nonce.values())
@@ -181,7 +247,9 @@ class ShardRuntime:
     def load_model_core(self, req: ShardLoadModelRequest) -> None:
         if not torch.cuda.is_available():
             raise RuntimeError("dnet_b200 needs a CUDA device: the shard forward has no CPU fallback")
-        _cabi.init(torch.cuda.current_device())
+        self._bind_thread_device()           # load may run on an executor thread (Shard.load_model)
+        self._device_index = int(torch.cuda.current_device())
+        _cabi.init(self._device_index)
         if self._wire_dtype_str != "bfloat16":
             raise ValueError("set DNET_TRANSPORT_WIRE_DTYPE=bf16: the wire dtype must equal the bf16 model dtype")
         lib = _cabi.load()
@@ -209,6 +277,7 @@ class ShardRuntime:
         if self.compute_stream is None:
             self.compute_stream = torch.cuda.Stream()
             self.compute_stream_ptr = int(self.compute_stream.cuda_stream)
+            self.comm_stream = torch.cuda.Stream()
         # fit mode with synthetic weights generates straight into HBM; everything else stages
         # the packed layer records in pinned host memory first
         self.stage_host = not (isinstance(self.model_metadata.source, SyntheticSource) and plan.mode == "fit")
@@ -263,11 +332,13 @@ class ShardRuntime:
                         break
                 if self.compute_stream is not None:
                     self.compute_stream.synchronize()
+                self.reap_releases(wait=True)
                 for ns in list(self._kv_by_nonce.values()) + self._ns_pool:
                     ns.free()
                 self._kv_by_nonce.clear()
                 self._ns_pool.clear()
                 self._kv_last_seen.clear()
+                self.lane_nonce.clear()
                 self.policy.clear()
                 self.policy = NoopPolicy(runtime=self, resident_windows=1)
                 self.model.destroy()
@@ -301,8 +372,7 @@ class ShardRuntime:
         self.policy.process(activation_msg)
 
     def _compute_worker(self) -> None:
-        if torch.cuda.is_available():
-            torch.cuda.set_device(torch.cuda.current_device())
+        self._bind_thread_device()
         while self.running:
             try:
                 activation_msg = self.activation_recv_queue.get(timeout=1.0)
@@ -336,8 +406,19 @@ class ShardRuntime:
         self._kv_last_seen[nonce] = time.perf_counter()
         return ns
 
+    def note_new_nonce(self, nonce: str) -> None:
+        """Transport saw the first frame of a nonce (reference adapters/ring.py:177-181 builds the KV right
+        there; here the compute thread does, in policy.process, so that all CUDA state of a shard is created
+        by the one thread bound to its device)."""
+        self._kv_last_seen.setdefault(nonce, time.perf_counter())
+
     def _recycle(self, ns: NonceState) -> None:
         """An expired nonce's KV pages, buffers and pinned result are kept for the next nonce."""
+        if ns.lane >= 0:
+            for lane, n in list(self.lane_nonce.items()):
+                if lane == ns.lane and self._kv_by_nonce.get(n) is None:
+                    self.lane_nonce.pop(lane, None)
+        ns.lane, ns.params, ns.hop_sent_event = -1, {}, None
         if ns.kv.max_tokens >= self.kv_cache_config.max_tokens and len(self._ns_pool) < 64:
             ns.drop_graphs()
             self._ns_pool.append(ns)
@@ -352,6 +433,12 @@ class ShardRuntime:
         self._kv_last_seen.pop(nonce, None)
         if ns is not None:
             self._recycle(ns)
+
+    def release_nonce_deferred(self, nonce: str) -> None:
+        """End of request from the transport: kernels of the nonce may still be queued on the compute
+        stream, so its KV only goes back to the pool through the TTL sweep (a recycled NonceState is
+        reset on the same stream, i.e. behind those kernels)."""
+        self._kv_last_seen[nonce] = time.perf_counter() - float(self._kv_ttl_s) - 1.0
 
     def start(self):
         self.running = True

@@ -145,6 +145,10 @@ int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, void* x_ino
                       const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
                       void* send_dst, uint32_t* send_flag, uint32_t send_seq, dn_stream s);
 int dn_step_error(dn_model* m, dn_stream s);
+/* 0, or the code of a timed-out bounded wait inside k_shard_step (2 ring, 3 grid barrier, 4 hop flag).  The word is
+ * sticky and the kernel reports it to the host as token_out = -(1000 + code); dn_step_error_clear resets it
+ * (asynchronous on s) once the caller has failed the request. */
+int dn_step_error_clear(dn_model* m, dn_stream s);
 /* per-SM row partition of the step kernel's four weight phases, [4][sms+1] (NULL: equal split); see
  * dnet_b200.shard.calibrate */
 int dn_step_set_bounds(dn_model* m, const int32_t* bounds_host);
