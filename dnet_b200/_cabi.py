@@ -110,6 +110,7 @@ _PROTOS = {
     "dn_enable_peer": (_i, [_i]),
     "dn_hop_send": (_i, [_vp, _vp, _sz, _vp, _u32, _vp]),
     "dn_hop_wait": (_i, [_vp, _u32, _u32, _vp, _vp]),
+    "dn_hop_ring_probe": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _i, _i, _u32, _vp, _vp]),
     "dn_pinned_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "dn_pinned_free": (_i, [_vp]),
     "dn_device_alloc": (_i, [_sz, C.POINTER(_vp)]),

@@ -1050,6 +1050,17 @@ extern "C" int dn_hop_wait(const uint32_t* flag, uint32_t seq, uint32_t timeout_
   return DN_OK;
 }
 
+// measurement hook: `iters` trips of a (bytes + flag) token around the ring on an otherwise unused lane; the origin
+// rank's *out_ns (device-accessible) = elapsed ns for all trips, measured on its own clock (see k_hop_ring_probe)
+extern "C" int dn_hop_ring_probe(const void* own_slot, const uint32_t* own_flag, void* next_slot, uint32_t* next_flag,
+                                 size_t bytes, uint32_t base_seq, int iters, int is_origin, uint32_t timeout_ms,
+                                 unsigned long long* out_ns, dn_stream s) {
+  if (!own_slot || !own_flag || !next_slot || !next_flag || iters <= 0 || (bytes % 16)) return fail(DN_EINVAL, "bad argument");
+  CK(launch(k_hop_ring_probe, dim3(1), dim3(512), 0, (cudaStream_t)s, false, (const uint4*)own_slot, own_flag, (uint4*)next_slot,
+            next_flag, (int)(bytes / 16), base_seq, iters, is_origin ? 1 : 0, (unsigned long long)timeout_ms * 1000000ull, out_ns));
+  return DN_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // layer swap / plumbing
 // ---------------------------------------------------------------------------------

@@ -675,4 +675,51 @@ __global__ void k_flag_wait(const uint32_t* flag, uint32_t seq, unsigned long lo
   }
 }
 
+// Direct measurement of the ring hop: a token (payload of `n16` uint4 + sequence flag) travels `iters` times
+// around the ring of GPUs, every rank running this kernel on one lane nobody else uses.  Each rank waits for
+// its own flag, copies the payload from its slot into the successor's slot with peer stores, fences at system
+// scope and releases the successor's flag -- exactly what the fused hop at the end of k_shard_step does.  The
+// origin rank times the whole trip on its own globaltimer (no cross-GPU clock offset involved):
+// one hop = elapsed / (iters * ring size).  Bounded spins: a dead peer ends the kernel with *out_ns = 0.
+__global__ void __launch_bounds__(512) k_hop_ring_probe(const uint4* __restrict__ own_slot, const uint32_t* own_flag,
+                                                        uint4* __restrict__ next_slot, uint32_t* next_flag, int n16,
+                                                        uint32_t base, int iters, int is_origin,
+                                                        unsigned long long timeout_ns, unsigned long long* out_ns) {
+  __shared__ int dead;
+  if (threadIdx.x == 0) dead = 0;
+  __syncthreads();
+  unsigned long long t0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int i = 0; i <= iters; ++i) {
+    // origin: iteration i first waits for the return of token i (none for i == 0); the others wait for token i+1
+    const uint32_t want = base + (uint32_t)(is_origin ? i : i + 1);
+    if (!(is_origin && i == 0) && !(!is_origin && i == iters)) {
+      if (threadIdx.x == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        for (;;) {
+          uint32_t v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(own_flag) : "memory");
+          if ((int32_t)(v - want) >= 0) break;
+          unsigned long long tn;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
+          if (tn - ts > timeout_ns) { dead = 1; break; }
+        }
+      }
+      __syncthreads();
+      if (dead) { if (threadIdx.x == 0 && out_ns) *out_ns = 0ull; return; }
+    }
+    if (i == iters) break;                       // origin: last return received; others: all tokens forwarded
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) next_slot[j] = __ldcg(own_slot + j);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(next_flag), "r"(base + (uint32_t)i + 1u) : "memory");
+  }
+  if (threadIdx.x == 0 && out_ns != nullptr) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    *out_ns = t1 - t0;
+  }
+}
+
 }  // namespace dn

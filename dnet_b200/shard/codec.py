@@ -64,6 +64,20 @@ class ActivationCodec:
             return None
         return None
 
+    def tokens_message(self, nonce: str, ids, **kw) -> ActivationMessage:
+        """What ``deserialize`` produces for a ``tokens`` frame, without the proto round trip: the ids staged
+        in the (pinned) input pool.  For in-process drivers of ``policy.process`` (warm-up, calibration)."""
+        ids = [int(t) for t in ids]
+        n = len(ids)
+        pid = self.runtime.input_pool.allocate_for_layer(layer_id=-1, dtype=torch.int32, shape=(n,))
+        if pid is None:
+            raise MemoryError("input pool exhausted")
+        self.runtime.input_pool.get_buffer(pid)[:n] = torch.tensor(ids, dtype=torch.int32)
+        return ActivationMessage(nonce=nonce, pool_id=pid, batch_size=1, shape=(n,), dtype="tokens", layer_id=-1,
+                                 timestamp=0, node_origin=kw.pop("node_origin", "api"),
+                                 callback_url=kw.pop("callback_url", "grpc://api:0"),
+                                 temperature=kw.pop("temperature", 0.0), **kw)
+
     def serialize(self, msg: ActivationMessage, transport_config=None) -> bytes:
         """Device tensor -> wire bytes in the wire dtype (device->host copy + sync)."""
         shaped = msg.tensor

@@ -4,6 +4,7 @@ and helper semantics are the reference's; the weight "version" is the data point
 layer's first tensor (the reference uses id() of the first array)."""
 from __future__ import annotations
 
+import bisect
 from abc import ABC, abstractmethod
 from typing import Any, Dict, List, Optional
 
@@ -55,70 +56,77 @@ class ComputePolicy(ABC):
     @abstractmethod
     def clear(self): ...
 
+    # ---- helpers shared by the fit / offload policies.  Behaviour per SURVEY.md section 8(a) row a5 and the
+    #      reference's policy tests (tests/subsystems/test_shard_policy_impl.py:163-257); written against that
+    #      behaviour, over this repo's data structures (device-pointer versions, HBM slot recycling).
     @staticmethod
     def _next_local_layers(s: List[int], after_layer: int, count: int) -> List[int]:
+        """The first ``count`` layers of the sorted local list that come after ``after_layer``."""
         if count <= 0:
             return []
-        for i, layer in enumerate(s):
-            if layer > after_layer:
-                return s[i:i + count]
-        return []
+        lo = bisect.bisect_right(s, after_layer)
+        return list(s[lo:lo + count])
 
     def _delta_swap_eviction(self, window_layers: List[int], resident: List[int]) -> int:
+        """sliding_fit: make room for ``window_layers`` inside a budget of ``window_size`` resident layers.
+        Of the resident layers that are not part of the new window, the most recent ones that still fit
+        beside it stay; the older ones are evicted from the cache (when nothing references them), unbound
+        from the model and forgotten as bound versions.  Returns how many layers were evicted."""
         budget = max(1, int(self.window_size or 1))
-        curr_set = set(window_layers)
-        prev_only = [lid for lid in resident if lid not in curr_set]
-        keep_quota = max(0, budget - len(window_layers))
-        idx = max(0, len(prev_only) - keep_quota)
-        evict_head = prev_only[:idx]
-        if not evict_head:
+        incoming = set(window_layers)
+        leftovers = [lid for lid in resident if lid not in incoming]       # oldest first, as the cache lists them
+        room = max(0, budget - len(window_layers))
+        victims = leftovers[:max(0, len(leftovers) - room)]
+        if not victims or self.weight_cache is None:
             return 0
-        evicted: List[int] = []
-        for lid in evict_head:
+        gone = []
+        for lid in victims:
             try:
-                if self.weight_cache and self.weight_cache.evict_layer(lid):
-                    evicted.append(lid)
+                if self.weight_cache.evict_layer(lid):
+                    gone.append(lid)
             except Exception:
-                continue
-        if evicted:
+                pass                                                       # still referenced / racing: keep it
+        if gone:
             try:
-                self.runtime.model.unload_layers(evicted)
-                for lid in evicted:
-                    self._bound_versions.pop(lid, None)
+                self.runtime.model.unload_layers(gone)
             except Exception:
-                pass
-        return len(evicted)
+                return len(gone)
+            for lid in gone:
+                self._bound_versions.pop(lid, None)
+        return len(gone)
 
     def _bind_layer_weights(self, window_layers: List[int], msg) -> Optional[Dict[str, Any]]:
-        """Bind weights for window layers if needed."""
-        fast_fit = len(self.runtime._assigned_sorted) <= self.window_size
-        if fast_fit and all(wl in self._bound_versions for wl in window_layers):
+        """Which tensors must be (re)bound before ``window_layers`` can run.
+
+        {}    nothing to do -- in particular the decode fast path: every local layer fits in the window and
+              all requested layers are already bound, so the weight cache is not even consulted;
+        dict  name -> tensor of every layer whose resident copy differs from the one the model is bound to
+              (each consulted layer now holds one more cache reference: the caller drops it after compute);
+        None  a layer could not be materialised: the message's input buffer has been released, give up."""
+        everything_fits = len(self.runtime._assigned_sorted) <= self.window_size
+        if everything_fits and self._bound_versions.keys() >= set(window_layers):
             return {}
-        to_bind: Dict[str, Any] = {}
-        for wl in window_layers:
-            if not self.weight_cache:
-                logger.error("Weight cache not initialized")
-                self.runtime.input_pool.release(msg.pool_id)
-                return None
-            weights = self.weight_cache.get_weight(wl)
+        cache = self.weight_cache
+        pending: Dict[str, Any] = {}
+        for lid in window_layers:
+            weights = cache.get_weight(lid) if cache else None
             if weights is None:
-                logger.error("Failed to load weights for layer %s", wl)
+                logger.error("Weight cache not initialized" if not cache else f"Failed to load weights for layer {lid}")
                 self.runtime.input_pool.release(msg.pool_id)
                 return None
-            current_version = self._get_weight_version(weights)
-            if self._bound_versions.get(wl) != current_version:
-                to_bind.update(weights)
-                self._bound_versions[wl] = current_version
-        return to_bind
+            version = self._get_weight_version(weights)
+            if self._bound_versions.get(lid) != version:
+                self._bound_versions[lid] = version
+                pending.update(weights)
+        return pending
 
     @staticmethod
     def _get_weight_version(weights: dict) -> int:
-        if not weights:
-            return -1
-        for k, v in weights.items():
-            if not k.startswith("_"):
-                try:
-                    return int(v.data_ptr())
-                except Exception:
-                    return id(v)
+        """Identity of a layer's resident copy: the device address of its first tensor (a reload into another
+        HBM slot changes it; the reference uses id() of the first array).  -1 for an empty record."""
+        for name, tensor in (weights or {}).items():
+            if name.startswith("_"):
+                continue                      # bookkeeping entries (_slot, _ready_event)
+            ptr = getattr(tensor, "data_ptr", None)
+            return int(ptr()) if ptr is not None else id(tensor)
         return -1

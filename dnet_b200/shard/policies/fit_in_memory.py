@@ -30,6 +30,7 @@ class FitInMemoryPolicy(ComputePolicy):
     def configure_policy_for_model(self, req) -> None:
         self._mode = "fit"
         self._run_arrays = {}            # tuple(run) -> ctypes int32 array handed to dn_shard_step
+        self.sched_entries_done = 0      # decode steps launched from schedule frames (progress signal for drivers)
         local_count = max(1, len(self.runtime.assigned_layers))
         requested_w = max(1, int(req.window_size))
         self.window_size = min(local_count, requested_w)
@@ -142,6 +143,7 @@ class FitInMemoryPolicy(ComputePolicy):
                         import time
                         now = time.perf_counter()
                     rt._kv_last_seen[nonce] = now
+                    self.sched_entries_done += 1
                 if not (len(rt._assigned_sorted) <= self.window_size):
                     self.weight_cache.decrease_references(run)
         except Exception as e:

@@ -195,6 +195,13 @@ int dn_hop_send(void* dst_slot, const void* src, size_t bytes, uint32_t* dst_fla
 int dn_hop_wait(const uint32_t* flag, uint32_t seq, uint32_t timeout_ms, uint32_t* err_flag,
                 dn_stream s);
 
+/* measurement hook for the ring-hop latency BASELINE.json's metric names: a (bytes + flag) token makes `iters` trips
+ * around the ring on a lane no request uses, every rank running this on its stream; the origin's *out_ns
+ * (device-accessible) receives the elapsed ns of all trips on ITS clock: one hop = out_ns / (iters * ring size). */
+int dn_hop_ring_probe(const void* own_slot, const uint32_t* own_flag, void* next_slot, uint32_t* next_flag,
+                      size_t bytes, uint32_t base_seq, int iters, int is_origin, uint32_t timeout_ms,
+                      unsigned long long* out_ns, dn_stream s);
+
 /* ---- layer swap: replaces LayerManager.load_layer_to_gpu / WeightCache materialise
  *      (reference utils/layer_manager.py:229-282, core/memory/weight_cache.py:68-196) */
 int dn_pinned_alloc(size_t bytes, void** host_ptr);         /* cudaHostAlloc (portable) */

@@ -48,15 +48,9 @@ def make_runtime(cfgd: dict, weights: Dict[str, torch.Tensor], layers: Sequence[
 
 def token_message(rt, nonce: str, ids: Sequence[int], **kw):
     """What ActivationCodec.deserialize produces for a "tokens" frame."""
-    from dnet_b200.core.types.messages import ActivationMessage
+    from dnet_b200.shard.codec import ActivationCodec
 
-    n = len(ids)
-    pid = rt.input_pool.allocate_for_layer(layer_id=-1, dtype=torch.int32, shape=(n,))
-    buf = rt.input_pool.get_buffer(pid)
-    buf[:n] = torch.tensor(list(ids), dtype=torch.int32)
-    return ActivationMessage(nonce=nonce, pool_id=pid, batch_size=1, shape=(n,), dtype="tokens", layer_id=-1,
-                             timestamp=0, node_origin="api", callback_url="grpc://api:0",
-                             temperature=kw.pop("temperature", 0.0), **kw)
+    return ActivationCodec(rt).tokens_message(nonce, ids, **kw)
 
 
 def forward_message(msg, use_bytes_rt=None):
