@@ -127,76 +127,125 @@ def peaks():
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path, timed on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_full_depth_run(cfg: dict, steps: int, warmup: int, budget_s: float):
-    """The CPU port on the WHOLE model (all layers + lm_head, ~15 GB of bf16 weights streamed per token):
-    nothing is extrapolated.  One layer's tensors are generated once and cloned per layer (distinct memory,
-    so every layer streams from DRAM like distinct weights would; values do not matter for timing)."""
+def _cpu_threads(m, H: int, L: int) -> int:
+    """use as many host threads as actually help: a bs=1 GEMV is DRAM-bound and oversubscribing a big
+    dual-socket box makes it slower, so probe a few counts on one projection and keep the best"""
     import torch
-    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV, make_weights, sample_greedy
 
-    t0 = time.perf_counter()
-    oc = OracleConfig.from_dict(cfg)
-    L, H, V = cfg["num_hidden_layers"], cfg["hidden_size"], cfg["vocab_size"]
-    w0 = make_weights(oc, 0, layers=range(1), with_api=False)
-    w = {}
-    for l in range(L):
-        for k, v in w0.items():
-            w[k.replace("layers.0.", f"layers.{l}.")] = v.clone() if l else v
-    g = torch.Generator().manual_seed(0)
-    w["model.embed_tokens.weight"] = torch.randn(V, H, generator=g).to(torch.bfloat16)
-    w["lm_head.weight"] = (torch.randn(V, H, generator=g) * 0.02).to(torch.bfloat16)
-    w["model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
-    log(f"cpu weights for {L} layers + head built in {time.perf_counter() - t0:.1f}s")
-    m = LlamaOracle(oc, w)
     ncpu = os.cpu_count() or 1
     probe_x = torch.randn(1, H).to(torch.bfloat16)
+    name = "model.layers.1.mlp.gate_proj.weight" if L > 1 else "model.layers.0.mlp.gate_proj.weight"
     best_t, best_n = None, ncpu
     for n_thr in sorted({min(ncpu, c) for c in (8, 16, 32, 64, 128, ncpu)}):
         torch.set_num_threads(n_thr)
         m.linear(probe_x, "model.layers.0.mlp.gate_proj.weight")
         ta = time.perf_counter()
         for _ in range(3):
-            m.linear(probe_x, "model.layers.1.mlp.gate_proj.weight" if L > 1 else "model.layers.0.mlp.gate_proj.weight")
+            m.linear(probe_x, name)
         dt = (time.perf_counter() - ta) / 3
         if best_t is None or dt < best_t:
             best_t, best_n = dt, n_thr
     torch.set_num_threads(best_n)
+    return best_n
+
+
+def cpu_full_depth_run(cfg: dict, steps: int, warmup: int, budget_s: float, weights=None, prompt=None):
+    """The CPU port on the WHOLE model (all layers + lm_head, ~15 GB of bf16 weights streamed per token):
+    nothing is extrapolated.  With ``weights`` (the very tensors the GPU arm runs, copied to the host) the
+    greedy tokens it produces are returned too, so the same leg is the full-depth parity witness.  Without,
+    one layer's tensors are generated once and cloned per layer (distinct memory, so every layer streams
+    from DRAM like distinct weights would; values do not matter for timing)."""
+    import torch
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV, make_weights, sample_greedy
+
+    t0 = time.perf_counter()
+    oc = OracleConfig.from_dict(cfg)
+    L, H, V = cfg["num_hidden_layers"], cfg["hidden_size"], cfg["vocab_size"]
+    if weights is None:
+        w0 = make_weights(oc, 0, layers=range(1), with_api=False)
+        w = {}
+        for l in range(L):
+            for k, v in w0.items():
+                w[k.replace("layers.0.", f"layers.{l}.")] = v.clone() if l else v
+        g = torch.Generator().manual_seed(0)
+        w["model.embed_tokens.weight"] = torch.randn(V, H, generator=g).to(torch.bfloat16)
+        w["lm_head.weight"] = (torch.randn(V, H, generator=g) * 0.02).to(torch.bfloat16)
+        w["model.norm.weight"] = torch.ones(H, dtype=torch.bfloat16)
+    else:
+        w = weights
+    log(f"cpu weights for {L} layers + head ready in {time.perf_counter() - t0:.1f}s")
+    m = LlamaOracle(oc, w)
+    threads = _cpu_threads(m, H, L)
     kv = {l: OracleKV() for l in range(L)}
-    gp = torch.Generator().manual_seed(1234)
-    ids = torch.randint(0, V, (PROMPT_LEN,), generator=gp, dtype=torch.int32)
-    x = m.embed(ids)
+    if prompt is None:
+        gp = torch.Generator().manual_seed(1234)
+        prompt = torch.randint(0, V, (PROMPT_LEN,), generator=gp).tolist()
+    x = m.embed(torch.tensor(prompt, dtype=torch.int32))
     for l in range(L):
-        x = m.apply_single_layer(l, x, kv[l])
-    tok, n, t_tot = 1, 0, 0.0
+        x = m.apply_single_layer(l, x, kv[l]).to(torch.bfloat16)
+    first = sample_greedy(m.lm_project(m.normalize(x)[-1:])[0], True, 0)
+    tok, n, t_tot = first.token_id, 0, 0.0
+    tokens, gaps = [tok], []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
         a = time.perf_counter()
         x = m.embed(torch.tensor([tok], dtype=torch.int32))
         for l in range(L):
             x = m.apply_single_layer(l, x, kv[l]).to(torch.bfloat16)   # per-layer cast to the wire dtype
-        tok = sample_greedy(m.lm_project(m.normalize(x))[0], True, 0).token_id
+        logits = m.lm_project(m.normalize(x))[0]
+        tok = sample_greedy(logits, True, 0).token_id
         b = time.perf_counter()
+        top2 = torch.topk(logits.to(torch.float32), 2).values
+        gaps.append(float(top2[0] - top2[1]) / max(float(top2[0].abs()) * 2.0 ** -8, 1e-30))   # top-1/top-2 gap in bf16 ulps
+        tokens.append(tok)
         if i >= warmup:
             t_tot += b - a
             n += 1
         if time.perf_counter() - t_start > budget_s and n >= 3:
             break
-    return n / t_tot, {"steps_timed": n, "ms_per_token": t_tot / n * 1e3, "threads": best_n, "host_cpus": ncpu,
-                       "layers": L, "extrapolated": False}
+    return n / t_tot, {"steps_timed": n, "ms_per_token": t_tot / n * 1e3, "threads": threads, "host_cpus": os.cpu_count() or 1,
+                       "layers": L, "extrapolated": False, "tokens": tokens, "gap_ulps": gaps}
 
 
-def cpu_baseline_leg(args, cfg: dict):
-    """cpu_baseline of our arm: the same full-depth CPU port, bounded to ~cpu_budget seconds of stepping."""
+def cpu_baseline_leg(args, cfg: dict, rt=None, prompt=None, gpu_tokens=None):
+    """cpu_baseline of our arm: the full-depth CPU port, bounded to ~cpu_budget seconds of stepping.  At N=1
+    it runs on the GPU arm's own weights (copied device -> host) and prompt, which makes it the full-depth
+    parity witness as well: its greedy tokens are compared with the GPU's, step by step until they part."""
+    weights = None
+    if rt is not None:
+        try:
+            weights = {}
+            for l in range(cfg["num_hidden_layers"]):
+                for k, v in rt.policy.weight_cache.cache[l][0].items():
+                    if not k.startswith("_"):
+                        weights["model." + k] = v.cpu()
+            for k, v in rt._api_tensors.items():
+                weights[("model." if not k.startswith("lm_head") else "") + k] = v.cpu()
+        except Exception as e:
+            log(f"could not copy the GPU arm's weights to the host ({e}); timing the CPU port on cloned layers")
+            weights = None
     try:
-        tps, detail = cpu_full_depth_run(cfg, 16, 1, budget_s=args.cpu_budget)
+        tps, detail = cpu_full_depth_run(cfg, 16, 0, budget_s=args.cpu_budget, weights=weights, prompt=prompt)
     except MemoryError as e:   # a box without ~17 GB of free host RAM
         log(f"cpu baseline skipped: {e}")
-        return None
+        return None, None
+    toks, gaps = detail.pop("tokens"), detail.pop("gap_ulps")
     cpu = {"value": tps, "unit": "tok/s", "cores": detail["threads"], "kind": "port",
            "sample": f"all {detail['layers']} layers + lm_head per step at a {PROMPT_LEN}-token context (nothing extrapolated), "
-                     f"{detail['steps_timed']} decode steps", "detail": detail}
+                     f"{detail['steps_timed']} decode steps" + (" on the GPU arm's weights" if weights is not None else ""),
+           "detail": detail}
     log("cpu_baseline:", json.dumps(cpu))
-    return cpu
+    parity = None
+    if weights is not None and gpu_tokens:
+        n = min(len(toks), len(gpu_tokens))
+        first_bad = next((i for i in range(n) if toks[i] != gpu_tokens[i]), None)
+        parity = {"what": "greedy token ids, GPU (k_shard_step through the ring transport) vs the CPU oracle on the same weights, "
+                          f"full depth ({detail['layers']} layers), prompt {PROMPT_LEN} tokens",
+                  "compared": n, "equal_prefix": n if first_bad is None else first_bad, "first_mismatch_step": first_bad,
+                  "oracle_gap_ulps_at_mismatch": (gaps[first_bad - 1] if first_bad else None) if first_bad is not None else None,
+                  "min_oracle_gap_ulps": min(gaps[:max(0, (first_bad if first_bad is not None else n) - 1)] or [None])}
+        log("full-depth parity:", json.dumps(parity))
+    return cpu, parity
 
 
 def run_reference(args, rank: int, world: int) -> None:
@@ -284,10 +333,9 @@ def single_gpu_extras(args, rt, cfg: dict, K: int, ms: float) -> dict:
     names = ["qkv_rope_append", "attention", "o_proj_residual", "gate_up_swiglu", "down_residual"]
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(0, cfg["vocab_size"], (PROMPT_LEN,), generator=g).tolist()
-    with rt._model_lock:
-        pass
-    rt.policy.process(ActivationCodec(rt).tokens_message("prof", prompt, req_logprobs=True))
-    rt.activation_send_queue.get(timeout=60)
+    # (the adapter's egress worker takes the emitted first token; the local:// sink drops it)
+    rt.policy.process(ActivationCodec(rt).tokens_message("prof", prompt, req_logprobs=True, callback_url="local://"))
+    rt.compute_stream.synchronize()
     nsp = rt.get_or_make_kv("prof")
     acc, reps = [0.0] * 5, 0
     out5 = (C.c_float * 5)()

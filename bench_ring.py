@@ -130,7 +130,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         mgr = api.manager
 
         def sink(msg):
-            got[msg.nonce].append((int(msg.token_id), float(msg.logprob)))
+            got.setdefault(msg.nonce, []).append((int(msg.token_id), float(msg.logprob)))
         ad.token_sink = sink
 
         async def send_prompts():
@@ -231,7 +231,12 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
 
     # ---- N=1 extras: per-kernel times, DRAM traffic of the dominant kernel, CPU baseline
     extras = B.single_gpu_extras(args, rt, cfg, K, ms) if world == 1 else {}
-    cpu = B.cpu_baseline_leg(args, cfg) if (rank == 0 and not args.no_cpu) else None
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu:
+        if world == 1:
+            cpu, parity = B.cpu_baseline_leg(args, cfg, rt=rt, prompt=prompts[0], gpu_tokens=[t for t, _ in got[nonces[0]]])
+        else:
+            cpu, parity = B.cpu_baseline_leg(args, cfg)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -281,6 +286,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
             "ring_hop_us": hop,
             "check": {"nonce0_token_after_steps": W + K, "token": check_token, "all_tokens_valid": tokens_ok,
+                      "oracle_full_depth": parity,
                       "note": "nonce 0's token after W+K decode steps: identical at every N and for both splits"},
         }
         B.emit(out)
