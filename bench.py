@@ -288,7 +288,7 @@ def _mlx_probe() -> dict:
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def measure_hop(rt, ad, dist, rank: int, world: int, iters: int = 2000):
+def measure_hop(rt, ad, barrier, rank: int, world: int, iters: int = 2000):
     """Ring-hop latency, measured directly: an 8 KiB activation + flag token travels `iters` times around the
     ring on a spare lane (dn_hop_ring_probe); the origin's globaltimer covers all trips, so no cross-GPU clock
     offset enters.  Returns microseconds per hop (payload stores + system-scope flag release -> acquire)."""
@@ -303,11 +303,11 @@ def measure_hop(rt, ad, dist, rank: int, world: int, iters: int = 2000):
     base = 0
     for nbytes, name in ((hop.hidden * 2, "activation_8k"), (16, "token_16b")):
         rt.compute_stream.synchronize()
-        dist.barrier()
+        barrier()
         _cabi.check(lib.dn_hop_ring_probe(hop.rx.slot(lane), hop.rx.flag(lane), hop.tx_slot(lane), hop.tx_flag(lane), nbytes,
                                           base, iters, 1 if rank == 0 else 0, 5000, out.data_ptr(), rt.compute_stream_ptr))
         rt.compute_stream.synchronize()
-        dist.barrier()
+        barrier()
         base += iters
         if rank == 0:
             ns = int(out[0].item())

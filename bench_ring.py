@@ -50,14 +50,22 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     from dnet_b200.utils.model import SyntheticSource
 
     dist = None
+    gloo = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG", "INFO")                  # NCCL's own log goes to stderr (stdout is guarded)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # Barriers and the few scalar reductions of the harness run over gloo, on the HOST: an NCCL barrier is a
+        # kernel that spins on the GPU (on the legacy default stream) until every rank arrives, and here ranks
+        # arrive at very different times while their shards must keep serving the ring.
+        gloo = dist.new_group(backend="gloo")
+        ok = torch.ones(1, device="cuda")
+        dist.all_reduce(ok)                                            # one NCCL collective: rank count check
+        assert int(ok.item()) == world
 
     def barrier():
         if dist is not None:
-            dist.barrier()
+            dist.barrier(group=gloo)
 
     PROMPT_LEN = B.PROMPT_LEN
     lib = _cabi.load()
@@ -141,7 +149,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                                                                                     repetition_penalty=1.0, min_p=0.0,
                                                                                     min_tokens_to_keep=1))
         api.call(send_prompts())
-        _wait(lambda: all(len(got[n]) >= 1 for n in nonces), 600, "first tokens (prefill)")
+        _wait(lambda: all(len(got[n]) >= 1 for n in nonces), 120, "first tokens (prefill)")
         log(f"prefilled {NS} nonces through the ring; first tokens {[got[n][0][0] for n in nonces]}")
     barrier()
 
@@ -161,11 +169,11 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         t0 = time.perf_counter()
         if last:
             lease_all(steps)
-        _wait(lambda: entries_done() >= base_entries + steps * NS, 1200, "schedule frames", poll=5e-5)
+        _wait(lambda: entries_done() >= base_entries + steps * NS, 180, "schedule frames", poll=5e-5)
         e1.record(stream)
         wall = None
         if last:
-            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 1200, "tokens", poll=2e-5)
+            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=2e-5)
             wall = time.perf_counter() - t0
         stream.synchronize()
         torch.cuda.synchronize()
@@ -188,15 +196,15 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     def allmax(x: float) -> float:
         if dist is None:
             return x
-        t = torch.tensor([x], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=gloo)
         return float(t.item())
 
     def allsum(x: int) -> int:
         if dist is None:
             return x
-        t = torch.tensor([x], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = torch.tensor([x], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=gloo)
         return int(t.item())
 
     ms = allmax(ms_local)
@@ -220,14 +228,14 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         e2.record(stream)
         if last:
             api.call(api.adapter.lease(nonces[0], K1, "local://"))
-        _wait(lambda: entries_done() >= base_e + K1, 600, "single-sequence schedule", poll=5e-5)
+        _wait(lambda: entries_done() >= base_e + K1, 120, "single-sequence schedule", poll=5e-5)
         e3.record(stream)
         if last:
-            _wait(lambda: len(got[nonces[0]]) >= base_t + K1, 600, "single-sequence tokens")
+            _wait(lambda: len(got[nonces[0]]) >= base_t + K1, 120, "single-sequence tokens")
         stream.synchronize()
         barrier()
         single_ms = allmax(e2.elapsed_time(e3)) / K1
-    hop = B.measure_hop(rt, ad, dist, rank, world) if world > 1 else None
+    hop = B.measure_hop(rt, ad, barrier, rank, world) if world > 1 else None
 
     # ---- N=1 extras: per-kernel times, DRAM traffic of the dominant kernel, CPU baseline
     extras = B.single_gpu_extras(args, rt, cfg, K, ms) if world == 1 else {}

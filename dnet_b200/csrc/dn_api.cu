@@ -48,6 +48,19 @@ static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
                               // harmful beyond -- 148 SMs x depth x 32 KB must stay well inside one L2 partition)
 static int g_sms = 0;
+// Internal one-off copies / fills (block tables, layer pointer tables, flag zeroing) go through a NON-BLOCKING
+// utility stream and are waited for on the host.  The legacy default stream is never used: a synchronous
+// cudaMemcpy on it would wait for whatever else the process has queued there -- e.g. a collective kernel of the
+// host framework spinning in a barrier -- and a shard must keep serving requests meanwhile.
+static cudaStream_t g_util = nullptr;
+static cudaError_t util_h2d(void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_util);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(g_util);
+}
+static cudaError_t util_fill0(void* dst, size_t bytes) {
+  cudaError_t e = cudaMemsetAsync(dst, 0, bytes, g_util);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(g_util);
+}
 static int g_device = -1;
 static bool g_capturing = false;
 static long long g_capture_launches = 0;
@@ -245,6 +258,7 @@ extern "C" int dn_init(int device) {
   if (p.major != 10) return fail(DN_EINVAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
   g_sms = p.multiProcessorCount;
   g_device = device;
+  if (!g_util) CK(cudaStreamCreateWithFlags(&g_util, cudaStreamNonBlocking));
   CK(init_kernel_attrs());
   return DN_OK;
 }
@@ -307,10 +321,10 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   CK(cudaMalloc(&m->logits_bf16, (size_t)cfg->vocab * 2));
   CK(cudaMalloc(&m->part, (size_t)tmax * cfg->n_heads * ns * PART_STRIDE * sizeof(float)));
   CK(cudaMalloc(&m->tickets, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
-  CK(cudaMemset(m->tickets, 0, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
+  CK(util_fill0(m->tickets, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
   CK(cudaMalloc(&m->head_part, (size_t)CTAS_PER_SM * g_sms * sizeof(HeadPartial)));
   CK(cudaMalloc(&m->inv_freq, (HD / 2) * sizeof(float)));
-  CK(cudaMemcpy(m->inv_freq, inv_freq_host, (HD / 2) * sizeof(float), cudaMemcpyHostToDevice));
+  CK(util_h2d(m->inv_freq, inv_freq_host, (HD / 2) * sizeof(float)));
   m->page_elems = (size_t)2 * cfg->n_kv_heads * PAGE * HD;
   m->layer_elems = m->page_elems * (size_t)cfg->kv_pool_pages;
   if (n_layers > 0 && cfg->kv_pool_pages > 0) {
@@ -323,7 +337,7 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   }
   if (m->kv_pool) {
     // never-written rows must be finite: the tcgen05 attention multiplies masked P (= 0) with whatever V holds
-    CK(cudaMemset(m->kv_pool, 0, m->layer_elems * n_layers * 2));
+    CK(util_fill0(m->kv_pool, m->layer_elems * n_layers * 2));
     m->tm_kv.resize(n_layers);
     m->tm_kv_ok = true;
     const long long rows = (long long)cfg->kv_pool_pages * 2 * cfg->n_kv_heads * PAGE;
@@ -335,11 +349,11 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   memset(m->mk_host.data(), 0, m->mk_host.size() * sizeof(MkLayer));
   for (int i = 0; i < n_layers; ++i) m->mk_host[i].kv_pool = m->kv_pool ? m->kv_pool + (size_t)i * m->layer_elems : nullptr;
   CK(cudaMalloc(&m->mk_dev, m->mk_host.size() * sizeof(MkLayer)));
-  CK(cudaMemcpy(m->mk_dev, m->mk_host.data(), m->mk_host.size() * sizeof(MkLayer), cudaMemcpyHostToDevice));
+  CK(util_h2d(m->mk_dev, m->mk_host.data(), m->mk_host.size() * sizeof(MkLayer)));
   CK(cudaMalloc(&m->xa, (size_t)H * 2));
   CK(cudaMalloc(&m->xb, (size_t)H * 2));
   CK(cudaMalloc(&m->mk_sync, 64));
-  CK(cudaMemset(m->mk_sync, 0, 64));
+  CK(util_fill0(m->mk_sync, 64));
   {
     const int qkvd = (cfg->n_heads + 2 * cfg->n_kv_heads) * HD;
     CK(cudaMalloc(&m->pf_xn, (size_t)TPF_MAX * H * 2));
@@ -348,9 +362,9 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
     CK(cudaMalloc(&m->pf_attn, (size_t)TPF_MAX * qd * 2));
     CK(cudaMalloc(&m->pf_h, (size_t)TPF_MAX * H * 2));
     CK(cudaMalloc(&m->pf_act, (size_t)TPF_MAX * cfg->ffn * 2));
-    CK(cudaMemset(m->pf_xn, 0, (size_t)TPF_MAX * H * 2));
-    CK(cudaMemset(m->pf_attn, 0, (size_t)TPF_MAX * qd * 2));
-    CK(cudaMemset(m->pf_act, 0, (size_t)TPF_MAX * cfg->ffn * 2));
+    CK(util_fill0(m->pf_xn, (size_t)TPF_MAX * H * 2));
+    CK(util_fill0(m->pf_attn, (size_t)TPF_MAX * qd * 2));
+    CK(util_fill0(m->pf_act, (size_t)TPF_MAX * cfg->ffn * 2));
     m->pf_ok = (H % 128 == 0) && (qd % 128 == 0) && (cfg->ffn % 128 == 0) && ((cfg->n_kv_heads * HD) % 128 == 0) &&
                true;
     for (int b = 0; b < 4 && m->pf_ok; ++b) {
@@ -399,7 +413,7 @@ extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_
   }
   MkLayer& ML = m->mk_host[it->second];
   for (int i = 0; i < DN_W_COUNT; ++i) ML.w[i] = L.w[i];
-  CK(cudaMemcpy(m->mk_dev + it->second, &ML, sizeof(MkLayer), cudaMemcpyHostToDevice));
+  CK(util_h2d(m->mk_dev + it->second, &ML, sizeof(MkLayer)));
   return DN_OK;
 }
 
@@ -443,9 +457,9 @@ extern "C" int dn_kv_create(dn_model* m, int max_tokens, dn_kv** out) {
   kv->max_tokens = np * PAGE;
   for (int i = 0; i < np; ++i) { kv->pages.push_back(m->free_pages.back()); m->free_pages.pop_back(); }
   CK(cudaMalloc(&kv->block_table, (size_t)np * sizeof(int32_t)));
-  CK(cudaMemcpy(kv->block_table, kv->pages.data(), (size_t)np * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(util_h2d(kv->block_table, kv->pages.data(), (size_t)np * sizeof(int32_t)));
   CK(cudaMalloc(&kv->st, sizeof(StepState)));
-  CK(cudaMemset(kv->st, 0, sizeof(StepState)));
+  CK(util_fill0(kv->st, sizeof(StepState)));
   *out = kv;
   return DN_OK;
 }
@@ -932,8 +946,8 @@ extern "C" int dn_step_set_bounds(dn_model* m, const int32_t* bounds_host) {
       if (b[i + 1] < b[i] || (b[i] % align[ph])) return fail(DN_EINVAL, "bounds of phase %d not monotone / aligned at %d", ph, i);
   }
   if (!m->mk_bounds) CK(cudaMalloc(&m->mk_bounds, (size_t)4 * n * sizeof(int)));
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(m->mk_bounds, bounds_host, (size_t)4 * n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());   // calibration only: no step kernel may be reading the old bounds
+  CK(util_h2d(m->mk_bounds, bounds_host, (size_t)4 * n * sizeof(int)));
   m->mk_bounds_on = true;
   return DN_OK;
 }
@@ -1004,8 +1018,7 @@ extern "C" int dn_hop_alloc(size_t bytes, void** dev_ptr) {
   if (!dev_ptr || bytes == 0) return fail(DN_EINVAL, "bad argument");
   cudaError_t e = cudaMalloc(dev_ptr, bytes);
   if (e != cudaSuccess) return fail(DN_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-  CK(cudaMemset(*dev_ptr, 0, bytes));
-  CK(cudaDeviceSynchronize());
+  CK(util_fill0(*dev_ptr, bytes));
   return DN_OK;
 }
 extern "C" int dn_hop_free(void* p) { if (p) CK(cudaFree(p)); return DN_OK; }

@@ -135,6 +135,9 @@ class HopSender:
             self.lib.dn_hop_close(self.flag_ptr)
 
 
+_PARKED_RECEIVERS: list = []
+
+
 class HopLink:
     """One shard's device-hop state: its own receive lanes and the ring successor's lanes.
 
@@ -188,12 +191,14 @@ class HopLink:
         return self.tx.flag_ptr + lane * 64
 
     def close(self) -> None:
+        """Unmap the successor's lanes.  Our own receive buffers were exported with CUDA IPC and the
+        predecessor may still have them mapped (shards of a ring stop in no particular order), so they are
+        parked instead of freed -- a few MB that the process returns at exit."""
         for t in (self.tx, self.tx_bulk):
             if t is not None:
                 t.close()
         self.tx = self.tx_bulk = None
-        self.rx.free()
-        self.rx_bulk.free()
+        _PARKED_RECEIVERS.extend((self.rx, self.rx_bulk))
 
 
 def even_split(num_layers: int, world: int) -> List[List[int]]:

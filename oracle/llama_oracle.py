@@ -132,14 +132,15 @@ class OracleKV:
 def mlx_affine_quantize(w: torch.Tensor, bits: int, group_size: int = 64):
     """Restatement of mlx.core.quantize (affine mode) along the last axis, as used by
     mlx_lm.models.cache.QuantizedKVCache (reference utils/model.py:505-554 selects it for
-    kv_bits 4/8).  Restated from the published algorithm, NOT verifiable in this tree (mlx is not
-    vendored): PARITY UNPINNED.  N4 groundwork -- the product does not build quantised KV yet.
-        per group: edge = the bound with the larger magnitude; scale = (max - min) / (2^bits - 1),
+    kv_bits 4/8).  Restated from the published algorithm of mlx's quantize kernels, NOT verifiable in
+    this tree (mlx is not vendored): PARITY UNPINNED.
+        per group: edge = the bound with the larger magnitude; scale = max((max - min) / (2^bits - 1), 1e-7),
         signed so that edge / scale >= 0, then snapped so that edge is exactly representable
         (scale = edge / round(edge / scale)); bias = edge (0 when round(edge / scale) == 0);
-        code = clip(round((w - bias) / scale), 0, 2^bits - 1).
-    Returns (codes uint8 [..., n], scales [..., n/group], biases [..., n/group]) with scales / biases in
-    w.dtype; dequantised value = scale * code + bias."""
+        code = clip(round((w - bias) / scale), 0, 2^bits - 1)   -- with the fp32 scale / bias;
+        the STORED scale / bias are rounded to w.dtype afterwards (what dequantisation then uses).
+    Returns (codes uint8 [..., n], scales [..., n/group], biases [..., n/group]); dequantised value =
+    scale * code + bias.  Rounding is round-half-to-even (rint), as torch.round."""
     n_bins = float((1 << bits) - 1)
     shape = w.shape
     g = w.to(torch.float32).reshape(*shape[:-1], shape[-1] // group_size, group_size)
@@ -151,9 +152,8 @@ def mlx_affine_quantize(w: torch.Tensor, bits: int, group_size: int = 64):
     q0 = torch.round(edge / scales)
     scales = torch.where(q0 != 0, edge / q0, scales)
     biases = torch.where(q0 == 0, torch.zeros_like(edge), edge)
-    scales, biases = scales.to(w.dtype), biases.to(w.dtype)             # stored in the cache dtype
-    codes = torch.clamp(torch.round((g - biases.to(torch.float32)) / scales.to(torch.float32)), 0, n_bins).to(torch.uint8)
-    return codes.reshape(shape), scales.squeeze(-1), biases.squeeze(-1)
+    codes = torch.clamp(torch.round((g - biases) / scales), 0, n_bins).to(torch.uint8)
+    return codes.reshape(shape), scales.squeeze(-1).to(w.dtype), biases.squeeze(-1).to(w.dtype)
 
 
 def mlx_affine_dequantize(codes: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64) -> torch.Tensor:
@@ -163,19 +163,23 @@ def mlx_affine_dequantize(codes: torch.Tensor, scales: torch.Tensor, biases: tor
 
 
 class OracleQuantKV(OracleKV):
-    """QuantizedKVCache semantics: every appended K / V row is quantised per group of 64 along
-    head_dim and attention runs on the dequantised values (mlx_lm quantized SDPA computes
-    q.(s*c+b) and p.(s*c+b) with fp32 accumulation)."""
+    """mlx_lm.models.cache.QuantizedKVCache semantics: every appended K / V row is quantised per group
+    of 64 along head_dim (codes + scale + bias in the cache dtype); ``update_and_fetch`` returns the
+    whole quantised cache, and attention runs on it with ``LlamaOracle.sdpa_quantized``.  Here the
+    dequantised fp32 view (scale * code + bias, exactly what quantized_matmul multiplies by) is kept
+    next to the packed parts."""
+
+    quantized = True
 
     def __init__(self, bits: int, group_size: int = 64) -> None:
         super().__init__()
         self.bits, self.group_size = int(bits), int(group_size)
-        self._parts: List[Tuple[torch.Tensor, ...]] = []
+        self.parts: List[Tuple[Tuple[torch.Tensor, ...], Tuple[torch.Tensor, ...]]] = []
 
     def update_and_fetch(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         kq = mlx_affine_quantize(k, self.bits, self.group_size)
         vq = mlx_affine_quantize(v, self.bits, self.group_size)
-        self._parts.append((kq, vq))
+        self.parts.append((kq, vq))
         kd = mlx_affine_dequantize(*kq, self.group_size)
         vd = mlx_affine_dequantize(*vq, self.group_size)
         self.k = kd if self.k is None else torch.cat([self.k, kd], dim=1)     # fp32 dequantised view
@@ -268,6 +272,29 @@ class LlamaOracle:
         p = torch.softmax(s, dim=-1)
         return self.T(p @ vf)
 
+    def sdpa_quantized(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offset: int) -> torch.Tensor:
+        """mlx_lm.models.base.quantized_scaled_dot_product_attention, which mlx_lm's
+        scaled_dot_product_attention dispatches to when the cache is a QuantizedKVCache:
+            queries *= scale                                   (in T: one rounding)
+            scores = quantized_matmul(queries, K^T)            (fp32 accumulate, output in T)
+            scores = where(causal mask, scores, finfo.min)
+            scores = softmax(scores, precise=True)             (fp32 math, output in T)
+            out    = quantized_matmul(scores, V)               (fp32 accumulate, output in T)
+        k, v are the dequantised fp32 views (scale * code + bias) of the quantised cache."""
+        Hq, Tn, hd = q.shape
+        n_kv, n, _ = k.shape
+        g = Hq // n_kv
+        qs = self.T(q.to(torch.float32) * (hd ** -0.5)).to(torch.float32)
+        kf = k.to(torch.float32).repeat_interleave(g, dim=0)
+        vf = v.to(torch.float32).repeat_interleave(g, dim=0)
+        s = self.T(qs @ kf.transpose(1, 2)).to(torch.float32)
+        if Tn > 1:
+            qpos = torch.arange(offset, offset + Tn)[:, None]
+            kpos = torch.arange(n)[None, :]
+            s = s.masked_fill(kpos > qpos, torch.finfo(self.dtype).min)
+        p = self.T(torch.softmax(s, dim=-1)).to(torch.float32)
+        return self.T(p @ vf)
+
     # -- BaseRingModel operator API ----------------------------------------
     def embed(self, ids: torch.Tensor) -> torch.Tensor:
         return self.w["model.embed_tokens.weight"][ids.long()]
@@ -304,7 +331,7 @@ class LlamaOracle:
         q = self.rope(q, offset)
         k = self.rope(k, offset)
         kk, vv = cache.update_and_fetch(k, v)
-        a = self.sdpa(q, kk, vv, offset)  # [H, T, hd]
+        a = (self.sdpa_quantized if getattr(cache, "quantized", False) else self.sdpa)(q, kk, vv, offset)  # [H, T, hd]
         a = a.transpose(0, 1).reshape(Tn, -1)
         r = self.linear(a, p + "self_attn.o_proj.weight")
         h = self.T(x.to(torch.float32) + r.to(torch.float32))

@@ -681,3 +681,60 @@ def test_quantised_kv_request_is_refused_unless_opted_in(tiny, cuda_lib, monkeyp
         assert [t for t, _, _ in out] == g["tokens"][:4].tolist()
     finally:
         rt.unload_model_core()
+
+
+def _teacher_forced_logits(cfgd, w, prompt, tokens, f64: bool):
+    """fp32 last-position logits of the oracle for every step, teacher-forced on ``tokens``"""
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+
+    oc = OracleConfig.from_dict(cfgd)
+    m = LlamaOracle(oc, w, exact_linear=not f64, f64_linear=f64)
+    kv = {l: OracleKV() for l in range(oc.num_hidden_layers)}
+    ids = torch.tensor(list(prompt), dtype=torch.int32)
+    out = []
+    for step in range(len(tokens)):
+        x = m.embed(ids)
+        for l in range(oc.num_hidden_layers):
+            x = m.apply_single_layer(l, x, kv[l]).to(torch.bfloat16)
+        out.append(m.lm_project(m.normalize(x[-1:]), return_fp32=True)[0].double())
+        ids = torch.tensor([int(tokens[step])], dtype=torch.int32)
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiny_llama", "tiny_qwen2_tied"])
+def test_gpu_is_as_close_to_the_f64_oracle_as_the_fp32_oracle_is(cuda_lib, name):
+    """The bounded end-to-end criterion.  bf16 pipelines are chaotic in the last bit, so "within 1e-3 of ONE
+    summation order" is not a property any implementation has end to end; what a correct implementation does
+    have is that it is no further from a high-precision-accumulate run of the same bf16 pipeline than another
+    correct summation order is.  Reference point: the oracle accumulating every dot product in float64.
+    Yardstick: the oracle accumulating in fp32 (the order the reference's MLX kernels are closest to).
+        per step     err(GPU, f64) <= 3.0 x max_step err(fp32, f64)
+        whole run    mean_step err(GPU, f64) <= 1.5 x mean_step err(fp32, f64)
+    err = max|a-b| / max|b| on the fp32 last-position logits, every step teacher-forced on the golden tokens."""
+    g = load_golden(name)
+    cfgd = g["config"]
+    w = oracle_weights(cfgd, g["wseed"])
+    steps = int(g["steps"])
+    toks = [int(t) for t in g["tokens"][:steps]]
+    ref64 = _teacher_forced_logits(cfgd, w, g["prompt"].tolist(), toks, f64=True)
+    ref32 = _teacher_forced_logits(cfgd, w, g["prompt"].tolist(), toks, f64=False)
+    rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]))
+    try:
+        ids = g["prompt"].tolist()
+        e_gpu, e_f32 = [], []
+        for step in range(steps):
+            rt.policy.process(token_message(rt, "crit", ids))
+            res = rt.activation_send_queue.get_nowait()
+            ns = rt._kv_by_nonce["crit"]
+            f32, _ = rt.model.head_logits(ns.x_view(len(ids)))
+            torch.cuda.synchronize()
+            e_gpu.append(rel_inf(f32.cpu(), ref64[step]))
+            e_f32.append(rel_inf(ref32[step], ref64[step]))
+            assert res.token_id == toks[step]
+            ids = [toks[step]]
+        worst_yard, mean_yard = max(e_f32), sum(e_f32) / steps
+        assert max(e_gpu) <= 3.0 * worst_yard, f"per-step: GPU {max(e_gpu):.3e} vs yardstick {worst_yard:.3e}"
+        assert sum(e_gpu) / steps <= 1.5 * mean_yard, f"mean: GPU {sum(e_gpu) / steps:.3e} vs yardstick {mean_yard:.3e}"
+        print(f"{name}: err(GPU,f64) mean {sum(e_gpu) / steps:.3e} max {max(e_gpu):.3e}; err(fp32,f64) mean {mean_yard:.3e} max {worst_yard:.3e}")
+    finally:
+        rt.unload_model_core()
