@@ -34,7 +34,7 @@ class WeightCache:
     def __init__(self, assigned_layers: List[int], model_metadata: Optional[ModelMetadata],
                  window_size: Optional[int] = None, prefetch_threads: int = 2, *, resident_windows: int = 2,
                  use_mxload_fastpath: bool = False, prefetch_mode: str = "off", layer_manager=None,
-                 stage_host: bool = True):
+                 stage_host: bool = True, keep_host_records: bool = True):
         self.assigned_layers = assigned_layers
         n = len(assigned_layers)
         if window_size is not None and window_size > 0:
@@ -52,7 +52,7 @@ class WeightCache:
 
             layer_manager = LayerManager(model_metadata, assigned_layers, thread_pool_size=int(prefetch_threads or 2),
                                          use_mxload_fastpath=bool(use_mxload_fastpath), prefetch_mode=prefetch_mode,
-                                         stage_host=stage_host)
+                                         stage_host=stage_host, keep_host_records=keep_host_records)
         self.layer_manager = layer_manager
         # does the manager's loader take an HBM slot to recycle?  (injected test managers take only the layer id)
         try:

@@ -43,6 +43,7 @@ class FitInMemoryPolicy(ComputePolicy):
             use_mxload_fastpath=self.runtime.compute_config.mxload_fastpath,
             prefetch_mode=self.runtime.compute_config.prefetch_mode,
             stage_host=self.runtime.stage_host,
+            keep_host_records=False,       # everything stays resident in HBM: staging records are dropped after the copy
         )
 
     # -- CUDA-graph fast path for single-token messages ----------------------------------

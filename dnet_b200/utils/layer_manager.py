@@ -2,11 +2,20 @@
 (reference src/dnet/utils/layer_manager.py:37-292, rebuilt for B200).
 
 The reference mmaps safetensors files, madvise()s the byte ranges of the next layer and
-copies tensor by tensor into MLX arrays.  Here each assigned layer is packed ONCE into a
+copies tensor by tensor into MLX arrays.  Here each assigned layer is packed into a
 page-locked host buffer (one contiguous record per layer, tensors at 256-byte aligned
 offsets) and a load is a single ``cudaMemcpyAsync`` of that record into an HBM layer slot
 on the prefetch stream (``dn_slot_prefetch``), followed by an event the compute stream
 waits on -- no host thread ever blocks on the copy.
+
+Where the record comes from:
+  * ``use_mxload_fastpath`` (the reference's switch for its per-layer ``mx.load``): the assigned layers are
+    repacked once into per-layer safetensors files (utils/repack.py, the reference's on-disk format) whose
+    data region IS the record, and a record is one sequential read disk -> pinned memory;
+  * otherwise tensor by tensor out of the mmapped checkpoint shards.
+How long it stays pinned: ``keep_host_records`` -- offload / sliding_fit keep the records (they are the
+backing store of every swap; ``host_record_budget`` > 0 caps how many stay pinned, least recently used
+first, the rest is re-read from disk), the fit policy drops a record as soon as its one H2D copy ran.
 """
 from __future__ import annotations
 
@@ -41,7 +50,7 @@ class LayerManager:
 
     def __init__(self, model_metadata: ModelMetadata, assigned_layers: List[int], thread_pool_size: int = 2, *,
                  use_mxload_fastpath: bool = False, prefetch_mode: str = "off", stage_host: bool = True,
-                 device: Optional[str] = None):
+                 device: Optional[str] = None, keep_host_records: bool = True, host_record_budget: int = 0):
         self.assigned_layers = set(assigned_layers)
         self.weight_info = model_metadata.weight_info
         self.source = model_metadata.source
@@ -57,6 +66,23 @@ class LayerManager:
         self._host: Dict[int, torch.Tensor] = {}   # layer -> pinned uint8 record
         self._host_lock = threading.Lock()
         self._prefetch_stream = None
+        self._keep_host = bool(keep_host_records)
+        self._host_budget = int(host_record_budget or int(os.environ.get("DNET_COMPUTE_HOST_RECORDS", "0") or 0))
+        self._host_lru: List[int] = []
+        self.repack_dir = None                # per-layer files (repack fast path), set below
+        self.record_reads = {"sequential": 0, "per-tensor": 0, "checkpoint": 0}
+        if self._use_mxload_fastpath and self.source is None and isinstance(model_metadata.path, os.PathLike):
+            try:
+                from dnet_b200.utils.repack import ensure_repacked_for_layers
+
+                t0 = time.perf_counter()
+                self.repack_dir, did = ensure_repacked_for_layers(str(model_metadata.path), sorted(self.assigned_layers),
+                                                                  md=model_metadata)
+                logger.info("[REPACK] %s per-layer files in %s (%.1fs)", "wrote" if did else "reusing", self.repack_dir,
+                            time.perf_counter() - t0)
+            except Exception as e:
+                logger.warning("repack fast path unavailable (%s); reading tensors from the checkpoint shards", e)
+                self.repack_dir = None
         for lid in sorted(self.assigned_layers):
             self._build_layout(lid)
 
@@ -82,18 +108,44 @@ class LayerManager:
         with self._host_lock:
             rec = self._host.get(layer_idx)
             if rec is not None:
+                if layer_idx in self._host_lru:
+                    self._host_lru.remove(layer_idx)
+                self._host_lru.append(layer_idx)
                 return rec
         nbytes = self._layer_bytes[layer_idx]
         rec = torch.empty(nbytes, dtype=torch.uint8)
         if torch.cuda.is_available():
             rec = rec.pin_memory()
-        for e in self._layout[layer_idx]:
-            wt = self.weight_info[layer_idx][e.suffix]
-            src = load_weight(wt, self.mapped_files, self.source)
-            rec[e.offset:e.offset + e.nbytes].copy_(src.contiguous().view(torch.uint8).reshape(-1))
+        how = None
+        if self.repack_dir is not None:
+            from dnet_b200.utils.repack import layer_file_name, read_layer_record
+
+            f = self.repack_dir / layer_file_name(layer_idx)
+            if f.exists():
+                try:
+                    how = read_layer_record(f, self._layout[layer_idx], rec)
+                except Exception as e:
+                    logger.warning("could not read %s (%s); falling back to the checkpoint shards", f, e)
+        if how is None:
+            how = "checkpoint"
+            for e in self._layout[layer_idx]:
+                wt = self.weight_info[layer_idx][e.suffix]
+                src = load_weight(wt, self.mapped_files, self.source)
+                rec[e.offset:e.offset + e.nbytes].copy_(src.contiguous().view(torch.uint8).reshape(-1))
+        self.record_reads[how] += 1
         with self._host_lock:
             self._host[layer_idx] = rec
+            self._host_lru.append(layer_idx)
+            if self._host_budget > 0:
+                while len(self._host_lru) > self._host_budget:      # LRU: re-read from disk when needed again
+                    self._host.pop(self._host_lru.pop(0), None)
         return rec
+
+    def drop_host_record(self, layer_idx: int) -> None:
+        with self._host_lock:
+            self._host.pop(layer_idx, None)
+            if layer_idx in self._host_lru:
+                self._host_lru.remove(layer_idx)
 
     def stage_all_to_host(self) -> int:
         """safetensors -> pinned host, once (offload mode calls this at load time)."""
@@ -178,6 +230,11 @@ class LayerManager:
         data = self.views(layer_idx, slot)
         data["_slot"] = slot
         data["_ready_event"] = ev.value
+        if not self._keep_host:
+            # fit mode: the layer stays resident in HBM and is never reloaded, so its pinned staging record
+            # (and, for quantised checkpoints, the dequantised copy in it) is released once the copy has run
+            _cabi.check(lib.dn_event_sync(ev.value))
+            self.drop_host_record(layer_idx)
         return data
 
     def close(self) -> None:
