@@ -48,7 +48,7 @@ class ModelCfg(C.Structure):
         ("hidden", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
         ("ffn", C.c_int32), ("vocab", C.c_int32), ("n_layers_total", C.c_int32), ("rms_eps", C.c_float),
         ("tie_embeddings", C.c_int32), ("dtype", C.c_int32), ("wire_dtype", C.c_int32),
-        ("kv_page_tokens", C.c_int32), ("kv_pool_pages", C.c_int32),
+        ("kv_page_tokens", C.c_int32), ("kv_pool_pages", C.c_int32), ("kv_bits", C.c_int32), ("kv_group", C.c_int32),
     ]
 
 

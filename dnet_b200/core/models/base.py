@@ -100,7 +100,7 @@ class BaseRingModel(ABC):
 
     # -- construction shared by subclasses --------------------------------------------
     def _create(self, cfg: dict, assigned_layers: List[int], inv_freq: torch.Tensor, kv_pool_pages: int,
-                wire_dtype: str = "bfloat16") -> None:
+                wire_dtype: str = "bfloat16", kv_bits: int = 0, kv_group: int = 64) -> None:
         self._lib = _cabi.load()
         dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
         _cabi.init(dev)
@@ -117,7 +117,9 @@ class BaseRingModel(ABC):
             n_kv_heads=cfg.get("num_key_value_heads", cfg["num_attention_heads"]), head_dim=hd,
             ffn=cfg["intermediate_size"], vocab=cfg["vocab_size"], n_layers_total=cfg["num_hidden_layers"],
             rms_eps=float(cfg.get("rms_norm_eps", 1e-5)), tie_embeddings=int(bool(cfg.get("tie_word_embeddings", False))),
-            dtype=0, wire_dtype=0, kv_page_tokens=64, kv_pool_pages=int(kv_pool_pages))
+            dtype=0, wire_dtype=0, kv_page_tokens=64, kv_pool_pages=int(kv_pool_pages), kv_bits=int(kv_bits),
+            kv_group=int(kv_group))
+        self.kv_bits = int(kv_bits)
         layers = sorted(assigned_layers or [])
         arr = (C.c_int32 * max(1, len(layers)))(*layers)
         inv = inv_freq.to(torch.float32).contiguous().cpu()

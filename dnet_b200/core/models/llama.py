@@ -41,7 +41,7 @@ class LlamaRingModel(BaseRingModel):
     model_type = "llama"
 
     def __init__(self, model_config: Any, assigned_layers: Optional[List[int]] = None, is_api_layer: bool = False,
-                 kv_pool_pages: int = 0, wire_dtype: str = "bfloat16"):
+                 kv_pool_pages: int = 0, wire_dtype: str = "bfloat16", kv_bits: int = 0, kv_group: int = 64):
         if is_api_layer and assigned_layers:
             raise RuntimeError("API layer doesn't handle layers")
         self.model_config = model_config
@@ -53,7 +53,7 @@ class LlamaRingModel(BaseRingModel):
         if self.config.get("mlp_bias", False):
             raise NotImplementedError("mlp_bias is not supported")
         self.layers = sorted(assigned_layers or [])
-        self._create(self.config, self.layers, rope_inv_freq(self.config), kv_pool_pages, wire_dtype)
+        self._create(self.config, self.layers, rope_inv_freq(self.config), kv_pool_pages, wire_dtype, kv_bits, kv_group)
 
     # -- operator API ----------------------------------------------------------------------
     def embed(self, x: torch.Tensor, stream=None) -> torch.Tensor:

@@ -3,6 +3,7 @@
 // scratch buffers, launch geometry, CUDA graphs, the NVLink hop and the pinned->HBM
 // layer-swap copies.  All arithmetic is in dn_kernels.cuh.
 #include "dn_kernels.cuh"
+#include "dn_kvquant.cuh"
 #include "dn_megakernel.cuh"
 #include "dn_gemm_tc.cuh"
 #include "../../include/dnet_b200.h"
@@ -164,6 +165,14 @@ struct dn_model {
   int* mk_bounds = nullptr;      // [4][sms+1] calibrated row partition of the step kernel (null: equal split)
   bool mk_bounds_on = false;
   unsigned int* mk_sync = nullptr;   // [0] barrier count, [1] generation, [2] error, [3] head ticket
+  // quantised KV (cfg.kv_bits 4 / 8): bf16 staging pool the append kernels write into + its block table,
+  // per-head score scratch of the two-pass attention, per-head arrival counters of the split exchange
+  bf16* kvq_stage = nullptr;
+  int32_t* kvq_stage_bt = nullptr;
+  float* kvq_scores = nullptr;
+  int kvq_score_stride = 0;
+  unsigned int* kvq_head_tk = nullptr;
+  size_t kv_layer_bytes = 0;         // bytes of one local layer's pages (bf16 or packed)
 };
 
 struct dn_kv {
@@ -325,8 +334,13 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   CK(cudaMalloc(&m->head_part, (size_t)CTAS_PER_SM * g_sms * sizeof(HeadPartial)));
   CK(cudaMalloc(&m->inv_freq, (HD / 2) * sizeof(float)));
   CK(util_h2d(m->inv_freq, inv_freq_host, (HD / 2) * sizeof(float)));
-  m->page_elems = (size_t)2 * cfg->n_kv_heads * PAGE * HD;
+  if (cfg->kv_bits != 0 && cfg->kv_bits != 4 && cfg->kv_bits != 8) { dn_model_destroy(m); return fail(DN_EINVAL, "kv_bits must be 0 (16-bit), 4 or 8"); }
+  if (cfg->kv_bits != 0 && cfg->kv_group != 64) { dn_model_destroy(m); return fail(DN_EINVAL, "quantised KV needs group size 64 (got %d)", cfg->kv_group); }
+  if (cfg->kv_bits != 0 && cfg->n_heads > g_sms) { dn_model_destroy(m); return fail(DN_EINVAL, "quantised KV: more q heads than SMs"); }
+  // elements of the bf16 layout, or the same number of BYTES / 2 for the packed layout (units are even-sized)
+  m->page_elems = cfg->kv_bits ? (size_t)2 * cfg->n_kv_heads * kvq_unit_bytes(cfg->kv_bits) / 2 : (size_t)2 * cfg->n_kv_heads * PAGE * HD;
   m->layer_elems = m->page_elems * (size_t)cfg->kv_pool_pages;
+  m->kv_layer_bytes = m->layer_elems * 2;
   if (n_layers > 0 && cfg->kv_pool_pages > 0) {
     cudaError_t e = cudaMalloc(&m->kv_pool, m->layer_elems * n_layers * 2);
     if (e != cudaSuccess) {
@@ -339,12 +353,23 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
     // never-written rows must be finite: the tcgen05 attention multiplies masked P (= 0) with whatever V holds
     CK(util_fill0(m->kv_pool, m->layer_elems * n_layers * 2));
     m->tm_kv.resize(n_layers);
-    m->tm_kv_ok = true;
+    m->tm_kv_ok = cfg->kv_bits == 0;       // the tcgen05 prefill attention reads bf16 pages through TMA
     const long long rows = (long long)cfg->kv_pool_pages * 2 * cfg->n_kv_heads * PAGE;
     for (int i = 0; i < n_layers && m->tm_kv_ok; ++i)
       m->tm_kv_ok = rows < (1ll << 31) && make_tmap(&m->tm_kv[i], m->kv_pool + (size_t)i * m->layer_elems, (int)rows, HD, PAGE) == DN_OK;
   }
   for (int p = cfg->kv_pool_pages - 1; p >= 0; --p) m->free_pages.push_back(p);
+  if (cfg->kv_bits) {
+    const size_t stage_elems = (size_t)KVQ_STAGE_PAGES * 2 * cfg->n_kv_heads * PAGE * HD;
+    CK(cudaMalloc(&m->kvq_stage, stage_elems * 2));
+    CK(util_fill0(m->kvq_stage, stage_elems * 2));
+    std::vector<int32_t> bt(65536);
+    for (size_t i = 0; i < bt.size(); ++i) bt[i] = (int32_t)(i % KVQ_STAGE_PAGES);
+    CK(cudaMalloc(&m->kvq_stage_bt, bt.size() * sizeof(int32_t)));
+    CK(util_h2d(m->kvq_stage_bt, bt.data(), bt.size() * sizeof(int32_t)));
+    CK(cudaMalloc(&m->kvq_head_tk, (size_t)cfg->n_heads * sizeof(unsigned int)));
+    CK(util_fill0(m->kvq_head_tk, (size_t)cfg->n_heads * sizeof(unsigned int)));
+  }
   m->mk_host.resize(n_layers > 0 ? n_layers : 1);
   memset(m->mk_host.data(), 0, m->mk_host.size() * sizeof(MkLayer));
   for (int i = 0; i < n_layers; ++i) m->mk_host[i].kv_pool = m->kv_pool ? m->kv_pool + (size_t)i * m->layer_elems : nullptr;
@@ -384,6 +409,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
   cudaFree(m->mk_bounds); cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
   cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
+  cudaFree(m->kvq_stage); cudaFree(m->kvq_stage_bt); cudaFree(m->kvq_scores); cudaFree(m->kvq_head_tk);
   delete m;
   return DN_OK;
 }
@@ -446,6 +472,7 @@ extern "C" int dn_bind_api(dn_model* m, const void* embed, const void* norm, con
 // ---------------------------------------------------------------------------------
 // per-nonce KV
 // ---------------------------------------------------------------------------------
+extern "C" int dn_kv_free(dn_kv* kv);
 extern "C" int dn_kv_create(dn_model* m, int max_tokens, dn_kv** out) {
   if (!m || !out || max_tokens <= 0) return fail(DN_EINVAL, "bad argument");
   const int np = (max_tokens + PAGE - 1) / PAGE;
@@ -456,10 +483,25 @@ extern "C" int dn_kv_create(dn_model* m, int max_tokens, dn_kv** out) {
   kv->m = m;
   kv->max_tokens = np * PAGE;
   for (int i = 0; i < np; ++i) { kv->pages.push_back(m->free_pages.back()); m->free_pages.pop_back(); }
-  CK(cudaMalloc(&kv->block_table, (size_t)np * sizeof(int32_t)));
-  CK(util_h2d(kv->block_table, kv->pages.data(), (size_t)np * sizeof(int32_t)));
-  CK(cudaMalloc(&kv->st, sizeof(StepState)));
-  CK(util_fill0(kv->st, sizeof(StepState)));
+  cudaError_t e = cudaMalloc(&kv->block_table, (size_t)np * sizeof(int32_t));
+  if (e == cudaSuccess) e = util_h2d(kv->block_table, kv->pages.data(), (size_t)np * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&kv->st, sizeof(StepState));
+  if (e == cudaSuccess) e = util_fill0(kv->st, sizeof(StepState));
+  if (e == cudaSuccess && m->cfg.kv_bits && m->kvq_score_stride < kv->max_tokens) {
+    // per-head score scratch of the two-pass quantised attention grows with the longest context a nonce may reach
+    float* nb = nullptr;
+    const int stride = (kv->max_tokens + 31) / 32 * 32;
+    e = cudaMalloc(&nb, (size_t)m->cfg.n_heads * stride * sizeof(float));
+    if (e == cudaSuccess) {
+      if (m->kvq_scores) { cudaDeviceSynchronize(); cudaFree(m->kvq_scores); }
+      m->kvq_scores = nb;
+      m->kvq_score_stride = stride;
+    }
+  }
+  if (e != cudaSuccess) {      // give everything back: the pool must not shrink on a failed create
+    dn_kv_free(kv);
+    return fail(DN_ECUDA, "dn_kv_create: %s", cudaGetErrorString(e));
+  }
   *out = kv;
   return DN_OK;
 }
@@ -521,6 +563,35 @@ extern "C" int dn_embed(dn_model* m, const int32_t* ids_dev, int T, void* x_out,
   return DN_OK;
 }
 
+// quantised KV: after the (unchanged) append kernels wrote the T new K/V rows as bf16 into the staging pool, quantise
+// them into the packed pool and run the two-pass quantised attention (dn_kvquant.cuh)
+static int kvq_append_and_attend(dn_model* m, int li, const bf16* q, bf16* attn_out, int T, dn_kv* kv, cudaStream_t s) {
+  const dn_model_cfg& c = m->cfg;
+  unsigned char* pool = reinterpret_cast<unsigned char*>(m->kv_pool) + (size_t)li * m->kv_layer_bytes;
+  // host mirror: longest context any of the T queries sees (a captured graph is replayed at growing contexts)
+  const int kv_len_max = g_capturing ? kv->max_tokens : kv->host_pos + T;
+  const size_t smem = ((size_t)((kv_len_max + 31) / 32 * 32) + AQ_WARPS * 132) * sizeof(float);
+  if (smem > 200 * 1024) return fail(DN_EINVAL, "quantised-KV attention outside the step kernel supports contexts up to ~50K tokens (got %d)", kv_len_max);
+  static size_t smem_set[2] = {0, 0};
+  const int bi = c.kv_bits == 8 ? 1 : 0;
+  if (smem > smem_set[bi]) {
+    const size_t want = smem > 48 * 1024 ? 200 * 1024 : 48 * 1024;
+    cudaError_t e = c.kv_bits == 8 ? cudaFuncSetAttribute(k_attn_q<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want)
+                                   : cudaFuncSetAttribute(k_attn_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) return fail(DN_ECUDA, "k_attn_q smem attribute: %s", cudaGetErrorString(e));
+    smem_set[bi] = want;
+  }
+  const dim3 ga(T, 2 * c.n_kv_heads), gq(c.n_heads, T);
+  if (c.kv_bits == 8) {
+    CK(launch(k_kv_quant_append<8>, ga, dim3(32), 0, s, false, (const bf16*)m->kvq_stage, pool, (const int32_t*)kv->block_table, (const StepState*)kv->st, c.n_kv_heads));
+    CK(launch(k_attn_q<8>, gq, dim3(AQ_WARPS * 32), smem, s, false, q, (const unsigned char*)pool, (const int32_t*)kv->block_table, (const StepState*)kv->st, attn_out, c.n_heads, c.n_kv_heads));
+  } else {
+    CK(launch(k_kv_quant_append<4>, ga, dim3(32), 0, s, false, (const bf16*)m->kvq_stage, pool, (const int32_t*)kv->block_table, (const StepState*)kv->st, c.n_kv_heads));
+    CK(launch(k_attn_q<4>, gq, dim3(AQ_WARPS * 32), smem, s, false, q, (const unsigned char*)pool, (const int32_t*)kv->block_table, (const StepState*)kv->st, attn_out, c.n_heads, c.n_kv_heads));
+  }
+  return DN_OK;
+}
+
 static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, cudaStream_t s, cudaEvent_t* evs = nullptr) {
   auto it = m->abs2local.find(abs_layer);
   if (it == m->abs2local.end()) return fail(DN_ENOENT, "Layer %d not hosted on this model instance", abs_layer);
@@ -536,13 +607,15 @@ static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, 
   q.x = x; q.ln_w = L.w[DN_W_LN1];
   q.wq = L.w[DN_W_Q]; q.wk = L.w[DN_W_K]; q.wv = L.w[DN_W_V];
   q.bq = L.w[DN_W_QB]; q.bk = L.w[DN_W_KB]; q.bv = L.w[DN_W_VB];
-  q.q_out = m->qbuf; q.kv_pool = pool; q.block_table = kv->block_table; q.st = kv->st;
+  const bool kvq = c.kv_bits != 0;
+  q.q_out = m->qbuf; q.kv_pool = kvq ? m->kvq_stage : pool; q.block_table = kvq ? m->kvq_stage_bt : kv->block_table; q.st = kv->st;
   q.inv_freq = m->inv_freq; q.n_heads = c.n_heads; q.n_kv = c.n_kv_heads; q.eps = c.rms_eps;
   if (evs) CK(cudaEventRecord(evs[0], s));
   CK(launch_gemv_T(T, q, q.nrows / 2, s));
   if (evs) CK(cudaEventRecord(evs[1], s));
 
-  CK(launch_attn(m, m->qbuf, pool, kv->block_table, kv->st, T, s));
+  if (kvq) { const int rc = kvq_append_and_attend(m, li, m->qbuf, m->attn, T, kv, s); if (rc) return rc; }
+  else CK(launch_attn(m, m->qbuf, pool, kv->block_table, kv->st, T, s));
   if (evs) CK(cudaEventRecord(evs[2], s));
 
   OpOProj o;
@@ -622,10 +695,15 @@ static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* k
   p.col0 = qd + kd; p.bias = L.w[DN_W_VB];
   CK(gemm_tc<EPI_STORE>(L.tm[2], L.tm[2], m->tm_xn, p, s));
   p.bias = nullptr;
-  k_rope_append<<<dim3(c.n_heads + 2 * c.n_kv_heads, T), 128, 0, s>>>(m->pf_qkv, m->pf_q, pool, kv->block_table, kv->st, m->inv_freq,
+  const bool kvq = c.kv_bits != 0;
+  k_rope_append<<<dim3(c.n_heads + 2 * c.n_kv_heads, T), 128, 0, s>>>(m->pf_qkv, m->pf_q, kvq ? m->kvq_stage : pool,
+                                                                        kvq ? m->kvq_stage_bt : kv->block_table, kv->st, m->inv_freq,
                                                                         c.n_heads, c.n_kv_heads);
   g_launches++;
-  if (g_tc_attn && m->tm_kv_ok && (m->G == 1 || m->G == 2 || m->G == 4 || m->G == 8)) {
+  if (kvq) {
+    const int rc = kvq_append_and_attend(m, li, m->pf_q, m->pf_attn, T, kv, s);
+    if (rc) return rc;
+  } else if (g_tc_attn && m->tm_kv_ok && (m->G == 1 || m->G == 2 || m->G == 4 || m->G == 8)) {
     AtParams a;
     a.q = m->pf_q; a.out = m->pf_attn; a.block_table = kv->block_table; a.st = kv->st;
     a.n_heads = c.n_heads; a.n_kv = c.n_kv_heads; a.T = T; a.err = err;
@@ -873,6 +951,12 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
     p.dbg = m->mk_dbg;
   }
   p.bar_gen = m->mk_sync + 4;
+  p.kv_bits = c.kv_bits;
+  p.kv_stage = m->kvq_stage;
+  p.sc_buf = m->kvq_scores;
+  p.sc_stride = m->kvq_score_stride;
+  p.head_tk = m->kvq_head_tk;
+  if (c.kv_bits && (!m->kvq_scores || m->kvq_score_stride < kv->max_tokens)) return fail(DN_EINVAL, "quantised KV: score scratch smaller than the nonce's capacity");
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
   const int attn_bytes = 8 * 132 * 4 + 64;                 // per-warp attention partials

@@ -24,6 +24,7 @@
 // Rounding points and summation structure per output row are fixed -> deterministic.
 #pragma once
 #include "dn_kernels.cuh"
+#include "dn_kvquant.cuh"
 
 namespace dn {
 
@@ -97,6 +98,12 @@ struct MkParams {
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
+  // quantised KV (dn_kvquant.cuh): 0 = bf16 pages; 4 / 8 = packed pages, two-pass attention
+  int kv_bits;
+  bf16* kv_stage;            // bf16 staging pool the q/k/v epilogue writes the new K/V row into
+  float* sc_buf;             // [n_heads][sc_stride] bf16-rounded scores of the current layer
+  int sc_stride;
+  unsigned int* head_tk;     // [n_heads] monotonic arrival counters: the splits of a head exchange (max, sum)
 };
 
 // ---------------------------------------------------------------------------------
@@ -749,6 +756,151 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
   }
 }
 
+// ---------------------------------------------------------------------------------
+// attention phase over a QUANTISED paged KV (dn_kvquant.cuh has the semantics).  Same task mapping as mk_attention
+// (one CTA per (q head, split), 8 warps take the split's 32-token tiles round-robin) but two passes, because
+// mlx_lm's quantised attention rounds scores AND probabilities to bf16:
+//   A  s_j = bf16(q'.dequant(K_j)) -> score scratch (global, L2-resident); per-warp max; CTA max and sum(exp);
+//      with S > 1 splits the CTAs of a head exchange (max, sum) through `part` + a monotonic arrival counter
+//   B  p_j = bf16(exp(s_j - M) / L); o += p_j * dequant(V_j); fixed-order sums -> deterministic
+// The new token's K/V row was written as bf16 into the staging pool by the q/k/v epilogue; the warp that owns the
+// last tile quantises it on the fly (every CTA of the GQA group computes the same codes) and the group's first
+// head also stores the packed row into the pool.
+// ---------------------------------------------------------------------------------
+template <int G, int BITS>
+__device__ __forceinline__ void mk_attention_q(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane,
+                                               int S, int tps, int li, unsigned int tk_base) {
+  const int pos = p.st->pos, kv_len = pos + 1;
+  const int n_tiles = (kv_len + 31) >> 5;
+  float* wpart = reinterpret_cast<float*>(scratch);           // [MK_CW][132]
+  const float scale = 0.08838834764831845f;
+  unsigned char* pool = reinterpret_cast<unsigned char*>(L.kv_pool);
+  const int task = blockIdx.x;
+  if (task >= p.n_heads * S) return;                           // CTA-uniform: no task for this CTA
+  const int head = task / S, sp = task % S, kvh = head / G;
+  const int tile0 = sp * tps, tile1 = min(n_tiles, (sp + 1) * tps);
+  float* scb = p.sc_buf + (size_t)head * p.sc_stride;
+  float qv[4], qsum;
+  {
+    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(p.qbuf + head * HD + lane * 4));
+    qv[0] = bf16r(__fmul_rn(bf_lo(u.x), scale)); qv[1] = bf16r(__fmul_rn(bf_hi(u.x), scale));
+    qv[2] = bf16r(__fmul_rn(bf_lo(u.y), scale)); qv[3] = bf16r(__fmul_rn(bf_hi(u.y), scale));
+    qsum = (qv[0] + qv[1]) + (qv[2] + qv[3]);
+  }
+  // the new token lives in the last tile; its owner quantises it from the staging pool
+  const int last_tile = n_tiles - 1, jnew = pos & 31;
+  const bool owns_new = last_tile >= tile0 && last_tile < tile1 && ((last_tile - tile0) % MK_CW) == cw;
+  float kc[4] = {0.f, 0.f, 0.f, 0.f}, vc[4] = {0.f, 0.f, 0.f, 0.f}, ksc = 0.f, kbi = 0.f, vsc = 0.f, vbi = 0.f;
+  if (owns_new) {
+    float w[4];
+    kvq_read_stage4(kvq_stage_row(p.kv_stage, pos, 0, kvh, p.n_kv), lane, w);
+    kvq_quantise_row<BITS>(w, kc, ksc, kbi);
+    kvq_read_stage4(kvq_stage_row(p.kv_stage, pos, 1, kvh, p.n_kv), lane, w);
+    kvq_quantise_row<BITS>(w, vc, vsc, vbi);
+    if (head % G == 0) {
+      const int pg = p.block_table[pos / PAGE];
+      kvq_store_row<BITS>(const_cast<unsigned char*>(kvq_unit<BITS>(pool, pg, 0, kvh, p.n_kv)), pos % PAGE, lane, kc, ksc, kbi);
+      kvq_store_row<BITS>(const_cast<unsigned char*>(kvq_unit<BITS>(pool, pg, 1, kvh, p.n_kv)), pos % PAGE, lane, vc, vsc, vbi);
+    }
+  }
+  // ---- pass A
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int tile = tile0 + cw; tile < tile1; tile += MK_CW) {
+    const int t0 = tile << 5, nt = min(32, kv_len - t0);
+    const unsigned char* ku = kvq_unit<BITS>(pool, p.block_table[t0 / PAGE], 0, kvh, p.n_kv);
+    const bool has_new = tile == last_tile;
+    float sc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      sc[j] = 0.f;
+      if (j < nt) {
+        float c[4], s1, b1;
+        if (has_new && j == jnew) { c[0] = kc[0]; c[1] = kc[1]; c[2] = kc[2]; c[3] = kc[3]; s1 = ksc; b1 = kbi; }
+        else { kvq_load_codes<BITS>(ku, (t0 % PAGE) + j, lane, c); kvq_load_sb<BITS>(ku, (t0 % PAGE) + j, lane, s1, b1); }
+        const float dot = fmaf(qv[0], c[0], fmaf(qv[1], c[1], fmaf(qv[2], c[2], qv[3] * c[3])));
+        sc[j] = fmaf(s1, dot, b1 * qsum);
+      }
+    }
+    transpose_reduce32(sc, lane);
+    const float s = (lane < nt) ? bf16r(sc[0]) : -INFINITY;
+    scb[t0 + lane] = s;
+    m = fmaxf(m, warp_max(s));
+  }
+  if (lane == 0) wpart[cw * 132 + 128] = m;
+  cbar_sync();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < MK_CW; ++w) M = fmaxf(M, wpart[w * 132 + 128]);
+  float l = 0.f;
+#pragma unroll 1
+  for (int tile = tile0 + cw; tile < tile1; tile += MK_CW) {
+    const float s = scb[(tile << 5) + lane];                   // this thread's own store
+    l += warp_sum(s == -INFINITY ? 0.f : exp2f((s - M) * LOG2E));
+  }
+  if (lane == 0) wpart[cw * 132 + 129] = l;
+  cbar_sync();
+  float Lsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < MK_CW; ++w) Lsum += wpart[w * 132 + 129];
+  if (S > 1) {
+    // exchange (max, sum) among the S co-resident CTAs of this head; merged in split order -> deterministic
+    float* pp = p.part + ((size_t)head * p.nsplit + sp) * PART_STRIDE;
+    if (threadIdx.x == 0) {
+      pp[130] = M; pp[131] = Lsum;
+      __threadfence();
+      atomicAdd(p.head_tk + head, 1u);
+      const unsigned int target = tk_base + (unsigned int)S * (unsigned int)(li + 1);
+      const unsigned long long t0 = gtimer();
+      unsigned it = 0;
+      while ((int)(ld_acquire_gpu(p.head_tk + head) - target) < 0) {
+        if ((++it & 255u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
+      }
+    }
+    cbar_sync();
+    float Mg = -INFINITY;
+    for (int s2 = 0; s2 < S; ++s2) Mg = fmaxf(Mg, __ldcg(p.part + ((size_t)head * p.nsplit + s2) * PART_STRIDE + 130));
+    float Lg = 0.f;
+    for (int s2 = 0; s2 < S; ++s2) {
+      const float ms = __ldcg(p.part + ((size_t)head * p.nsplit + s2) * PART_STRIDE + 130);
+      if (ms != -INFINITY) Lg = fmaf(__ldcg(p.part + ((size_t)head * p.nsplit + s2) * PART_STRIDE + 131), exp2f((ms - Mg) * LOG2E), Lg);
+    }
+    M = Mg; Lsum = Lg;
+  }
+  const float invL = 1.0f / Lsum;
+  // ---- pass B
+  float o[4] = {0.f, 0.f, 0.f, 0.f}, ob = 0.f;
+#pragma unroll 1
+  for (int tile = tile0 + cw; tile < tile1; tile += MK_CW) {
+    const int t0 = tile << 5, nt = min(32, kv_len - t0);
+    const unsigned char* vu = kvq_unit<BITS>(pool, p.block_table[t0 / PAGE], 1, kvh, p.n_kv);
+    const bool has_new = tile == last_tile;
+    const float sl = scb[t0 + lane];
+    const float pl = (lane < nt) ? bf16r(exp2f((sl - M) * LOG2E) * invL) : 0.f;
+    for (int j = 0; j < nt; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pl, j);
+      float c[4], s1, b1;
+      if (has_new && j == jnew) { c[0] = vc[0]; c[1] = vc[1]; c[2] = vc[2]; c[3] = vc[3]; s1 = vsc; b1 = vbi; }
+      else { kvq_load_codes<BITS>(vu, (t0 % PAGE) + j, lane, c); kvq_load_sb<BITS>(vu, (t0 % PAGE) + j, lane, s1, b1); }
+      const float ws = pj * s1;
+      o[0] = fmaf(ws, c[0], o[0]); o[1] = fmaf(ws, c[1], o[1]); o[2] = fmaf(ws, c[2], o[2]); o[3] = fmaf(ws, c[3], o[3]);
+      ob = fmaf(pj, b1, ob);
+    }
+  }
+  cbar_sync();                                                 // everyone is done with wpart[..][128/129]
+  *reinterpret_cast<float4*>(wpart + cw * 132 + lane * 4) = make_float4(o[0] + ob, o[1] + ob, o[2] + ob, o[3] + ob);
+  cbar_sync();
+  if (threadIdx.x < HD) {
+    const int d = threadIdx.x;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < MK_CW; ++w) acc += wpart[w * 132 + d];
+    if (S == 1) p.attn[head * HD + d] = __float2bfloat16_rn(acc);
+    else p.part[((size_t)head * p.nsplit + sp) * PART_STRIDE + d] = acc;
+  }
+  cbar_sync();
+}
+
 // o_proj staging = merge of the attention splits (fixed order -> deterministic) straight into the
 // shared activation vector: every CTA does it redundantly from L2 (nact x 132 floats per head),
 // which removes the ticket + last-CTA merge + one more round trip from the critical path.
@@ -758,6 +910,22 @@ __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p)
   mk_attn_geometry(p, kv_len, nact, tps);
   if (nact == 1) {                       // the attention CTAs already wrote the normalised heads
     mk_stage_copy(xs, p.attn, p.n_heads * HD);
+    return;
+  }
+  if (p.kv_bits != 0) {
+    // quantised KV: every split's partial is already normalised by the head's global (max, sum): out = bf16(sum of partials)
+    for (int i = threadIdx.x; i < p.n_heads * 32; i += MK_CTHREADS) {
+      const int head = i >> 5, l4 = i & 31;
+      const float* hp = p.part + ((size_t)head * p.nsplit) * PART_STRIDE + l4 * 4;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int s2 = 0; s2 < nact; ++s2) {          // fixed order -> deterministic
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(hp + (size_t)s2 * PART_STRIDE));
+        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+      }
+      __align__(8) bf16 ob[4] = {__float2bfloat16_rn(a0), __float2bfloat16_rn(a1), __float2bfloat16_rn(a2), __float2bfloat16_rn(a3)};
+      *reinterpret_cast<uint2*>(xs + head * HD + l4 * 4) = *reinterpret_cast<const uint2*>(ob);
+    }
+    cbar_sync();
     return;
   }
   // (1) all (m, l) pairs in one parallel round trip -> shared memory (behind the activation vector)
@@ -918,7 +1086,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   int att_S, att_tps;
   mk_attn_geometry(p, pos + 1, att_S, att_tps);
   const int att_tile0 = ((int)blockIdx.x % att_S) * att_tps + cw;        // this warp's first tile (if the CTA has an attention task)
-  const bool att_has = (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
+  const bool att_has = p.kv_bits == 0 && (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
+  // quantised KV: value of this CTA's head counter before any arrival of this launch (arrivals happen after the first grid barrier)
+  const unsigned int tk_base = (p.kv_bits != 0 && (int)blockIdx.x < p.n_heads * att_S) ? __ldcg(p.head_tk + (int)blockIdx.x / att_S) : 0u;
   const int att_phys0 = att_has ? p.block_table[(att_tile0 << 5) / PAGE] : 0;
   cbar_sync();
   const int tok_in = p.token_in != nullptr ? __ldcg(p.token_in) : p.st->token;
@@ -965,8 +1135,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       if (kind == 0) {
         p.qbuf[hrow * HD + dim] = __float2bfloat16_rn(o);
       } else {
-        const size_t off = (((size_t)page_pos * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
-        L.kv_pool[off] = __float2bfloat16_rn(o);
+        // quantised KV: the bf16 row goes to the staging pool; the attention phase quantises and appends it
+        bf16* wpool = p.kv_bits ? p.kv_stage : L.kv_pool;
+        const int wpage = p.kv_bits ? (pos / PAGE) % KVQ_STAGE_PAGES : page_pos;
+        const size_t off = (((size_t)wpage * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
+        wpool[off] = __float2bfloat16_rn(o);
       }
     });
     MK_STAMP(2);
@@ -974,7 +1147,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     MK_STAMP(3);
 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
-    mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
+    if (p.kv_bits == 8) mk_attention_q<G, 8>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
+    else if (p.kv_bits == 4) mk_attention_q<G, 4>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
+    else mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
     mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(5);

@@ -262,18 +262,12 @@ class ShardRuntime:
         local_count = max(1, len(self.assigned_layers))
         plan: PolicyPlan = plan_policy(local_count=local_count, requested_w=int(req.window_size),
                                        residency_size=int(req.residency_size), topology_config=self._topology_settings)
+        # kv_bits "4bit" / "8bit" (the reference API's defaults, api/models.py:316,342) select the affine group-64
+        # quantised cache (reference runtime.py:204-214 -> utils/model.py:505-554); "fp16" the 16-bit cache
         kv = (req.kv_bits or "").strip().lower()
-        if kv in ("4bit", "8bit"):
-            # The reference's API defaults ask for a quantised KV cache (api/models.py:316,342).  It is not
-            # built here; results with a 16-bit cache differ from the reference's quantised-cache results,
-            # so this is refused unless the operator opts in explicitly.
-            import os
-            if os.environ.get("DNET_KV_QUANT_FALLBACK", "").strip().lower() != "fp16":
-                raise NotImplementedError("quantised KV (kv_bits 4bit/8bit) is not built yet; request kv_bits='fp16' "
-                                          "or set DNET_KV_QUANT_FALLBACK=fp16 to serve such requests with a 16-bit cache")
-            logger.warning("kv_bits=%s requested: serving with a 16-bit KV cache (DNET_KV_QUANT_FALLBACK=fp16); "
-                           "outputs differ from a quantised cache", kv)
-        self.kv_cache_config.mode = "fp16"
+        kv_bits = {"4bit": 4, "8bit": 8}.get(kv, 0)
+        self.kv_cache_config.mode = kv if kv_bits else "fp16"
+        self.kv_cache_config.bits = kv_bits or self.kv_cache_config.bits
         if self.compute_stream is None:
             self.compute_stream = torch.cuda.Stream()
             self.compute_stream_ptr = int(self.compute_stream.cuda_stream)
@@ -290,7 +284,8 @@ class ShardRuntime:
         pages = int(settings.kv_cache.pool_pages) or max(1, (self.kv_cache_config.max_tokens + 63) // 64) * 8
         self.model = get_ring_model(self.model_metadata.model_type, self.model_metadata.model_config,
                                     assigned_layers=self.assigned_layers, is_api_layer=False,
-                                    kv_pool_pages=pages, wire_dtype=self._wire_dtype_str)
+                                    kv_pool_pages=pages, wire_dtype=self._wire_dtype_str, kv_bits=kv_bits,
+                                    kv_group=int(self.kv_cache_config.group_size))
         self.model.apply_quantization_from_config(self.model_metadata.model_config, model_metadata=self.model_metadata)
         # embed / norm / head iff this shard owns layer 0 / the last layer (reference runtime.py:263-273)
         has_start = 0 in self.assigned_layers

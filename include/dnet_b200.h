@@ -70,6 +70,9 @@ typedef struct dn_model_cfg {
   int32_t wire_dtype;      /* must equal dtype (mixed wire dtype) */
   int32_t kv_page_tokens;  /* 64 */
   int32_t kv_pool_pages;   /* pages in the shard's KV pool (shared by all nonces) */
+  int32_t kv_bits;         /* 0: 16-bit KV (mlx_lm KVCache); 4 / 8: affine-quantised KV (QuantizedKVCache,
+                              reference utils/model.py:505-554 -- the API's default kv_bits) */
+  int32_t kv_group;        /* quantisation group along head_dim: 64 */
 } dn_model_cfg;
 
 /* ---- process / device -------------------------------------------------- */

@@ -28,7 +28,7 @@ def oracle_weights(cfgd: dict, wseed: int, layers=None):
 
 def make_runtime(cfgd: dict, weights: Dict[str, torch.Tensor], layers: Sequence[int], *, shard_id="s0",
                  window_size: Optional[int] = None, residency_size: Optional[int] = None, cuda_graphs: bool = True,
-                 max_tokens: int = 512, megakernel: bool = True):
+                 max_tokens: int = 512, megakernel: bool = True, kv_bits: str = "fp16"):
     """A ShardRuntime loaded through the reference-facing path (load_model_core)."""
     from dnet_b200.shard.models import ShardLoadModelRequest
     from dnet_b200.shard.runtime import ShardRuntime
@@ -41,7 +41,7 @@ def make_runtime(cfgd: dict, weights: Dict[str, torch.Tensor], layers: Sequence[
     n = len(layers)
     req = ShardLoadModelRequest(model_path=HostDictSource(weights, cfgd), total_layers=cfgd["num_hidden_layers"],
                                 layers=list(layers), window_size=window_size or n,
-                                residency_size=residency_size or (window_size or n), kv_bits="fp16")
+                                residency_size=residency_size or (window_size or n), kv_bits=kv_bits)
     rt.load_model_core(req)
     return rt
 

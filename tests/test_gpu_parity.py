@@ -654,42 +654,13 @@ def test_mlx_quantised_checkpoint_runs_like_its_dequantised_weights(tiny, cuda_l
         rt.unload_model_core()
 
 
-@pytest.mark.gpu
-def test_quantised_kv_request_is_refused_unless_opted_in(tiny, cuda_lib, monkeypatch):
-    """The reference API defaults to kv_bits 4bit/8bit (api/models.py:316,342); a 16-bit cache gives
-    different numbers, so the request fails loudly unless DNET_KV_QUANT_FALLBACK=fp16 is set."""
-    from dnet_b200.shard.models import ShardLoadModelRequest
-    from dnet_b200.shard.runtime import ShardRuntime
-    from dnet_b200.utils.model import HostDictSource
-    g, w = tiny
-    cfgd = g["config"]
-    L = cfgd["num_hidden_layers"]
-
-    def load(rt):
-        rt.load_model_core(ShardLoadModelRequest(model_path=HostDictSource(w, cfgd), total_layers=L, layers=list(range(L)),
-                                                 window_size=L, residency_size=L, kv_bits="8bit"))
-
-    monkeypatch.delenv("DNET_KV_QUANT_FALLBACK", raising=False)
-    with pytest.raises(NotImplementedError):
-        load(ShardRuntime(shard_id="kvq"))
-    monkeypatch.setenv("DNET_KV_QUANT_FALLBACK", "fp16")
-    rt = ShardRuntime(shard_id="kvq2")
-    rt.kv_cache_config.max_tokens = 256
-    load(rt)
-    try:
-        out = ring_generate([rt], "n", g["prompt"].tolist(), 4)
-        assert [t for t, _, _ in out] == g["tokens"][:4].tolist()
-    finally:
-        rt.unload_model_core()
-
-
-def _teacher_forced_logits(cfgd, w, prompt, tokens, f64: bool):
+def _teacher_forced_logits(cfgd, w, prompt, tokens, f64: bool, kv_bits: int = 0):
     """fp32 last-position logits of the oracle for every step, teacher-forced on ``tokens``"""
-    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV
+    from oracle.llama_oracle import LlamaOracle, OracleConfig, OracleKV, OracleQuantKV
 
     oc = OracleConfig.from_dict(cfgd)
     m = LlamaOracle(oc, w, exact_linear=not f64, f64_linear=f64)
-    kv = {l: OracleKV() for l in range(oc.num_hidden_layers)}
+    kv = {l: (OracleQuantKV(kv_bits) if kv_bits else OracleKV()) for l in range(oc.num_hidden_layers)}
     ids = torch.tensor(list(prompt), dtype=torch.int32)
     out = []
     for step in range(len(tokens)):
