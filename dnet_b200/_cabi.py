@@ -91,6 +91,7 @@ _PROTOS = {
     "dn_shard_step_hop": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _u32, _vp, _vp, _vp, _u32, _vp]),
     "dn_step_error": (_i, [_vp, _vp]),
     "dn_step_error_clear": (_i, [_vp, _vp]),
+    "dn_debug_scratch": (_i, [_vp, _i, _vp, _sz, _vp]),
     "dn_step_set_bounds": (_i, [_vp, C.POINTER(C.c_int32)]),
     "dn_step_debug": (_i, [_vp, C.POINTER(C.c_uint64), _sz, _vp]),
     "dn_layer_forward_timed": (_i, [_vp, _i, _vp, _i, _vp, _vp, C.POINTER(C.c_float)]),

@@ -1045,6 +1045,17 @@ extern "C" int dn_step_error(dn_model* m, dn_stream s) {
   return (int)v;
 }
 
+// debugging / parity bisection: copy one of the per-op path's scratch buffers of the LAST chunk to the host
+// (which: 0 q after RoPE [tmax][n_heads*128], 1 attention output, 2 h = x + o_proj [tmax][H], 3 SwiGLU output [tmax][ffn])
+extern "C" int dn_debug_scratch(dn_model* m, int which, void* host_out, size_t bytes, dn_stream s) {
+  if (!m || !host_out) return fail(DN_EINVAL, "null argument");
+  const bf16* src = which == 0 ? m->qbuf : which == 1 ? m->attn : which == 2 ? m->hbuf : which == 3 ? m->act : nullptr;
+  if (!src) return fail(DN_EINVAL, "unknown scratch buffer %d", which);
+  CK(cudaMemcpyAsync(host_out, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  CK(cudaStreamSynchronize((cudaStream_t)s));
+  return DN_OK;
+}
+
 // the error word is sticky (every later step reports it): clear it once the failed request was dropped
 extern "C" int dn_step_error_clear(dn_model* m, dn_stream s) {
   if (!m) return fail(DN_EINVAL, "null model");

@@ -152,6 +152,9 @@ int dn_step_error(dn_model* m, dn_stream s);
  * sticky and the kernel reports it to the host as token_out = -(1000 + code); dn_step_error_clear resets it
  * (asynchronous on s) once the caller has failed the request. */
 int dn_step_error_clear(dn_model* m, dn_stream s);
+/* parity bisection hook: copy a scratch buffer of the per-op path's LAST chunk to the host (0 q after RoPE,
+ * 1 attention output, 2 h = x + o_proj, 3 SwiGLU output); synchronises s */
+int dn_debug_scratch(dn_model* m, int which, void* host_out, size_t bytes, dn_stream s);
 /* per-SM row partition of the step kernel's four weight phases, [4][sms+1] (NULL: equal split); see
  * dnet_b200.shard.calibrate */
 int dn_step_set_bounds(dn_model* m, const int32_t* bounds_host);
