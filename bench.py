@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--split", default="balanced", choices=["balanced", "equal"],
                     help="N>1: contiguous layer split balanced by streamed bytes (lm_head counted) or equal layer counts")
     ap.add_argument("--no-single", action="store_true", help="skip the single-sequence latency view")
+    ap.add_argument("--head-tp", default="auto", choices=["auto", "on", "off"],
+                    help="N>1: lm_head tensor-parallel over the ring's shards (auto: rings of >= 4 shards)")
     ap.add_argument("--sched-rounds", type=int, default=8, help="decode rounds per schedule frame (head shard's RingAdapter)")
     ap.add_argument("--sched-depth", type=int, default=4, help="schedule frames in flight")
     ap.add_argument("--no-cpu", action="store_true")

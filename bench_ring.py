@@ -74,9 +74,12 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         cfg["num_hidden_layers"] = args.layers
     L, H = cfg["num_hidden_layers"], cfg["hidden_size"]
     K, W = args.steps, args.warmup
-    NS = (world if args.in_flight <= 0 else args.in_flight)
-    if args.split == "equal" or world == 1:
-        split = even_split(L, world)
+    tp_wanted = world >= 2 and (args.head_tp == "on" or (args.head_tp == "auto" and world >= 4))
+    # sequences in flight: one per shard keeps a plain ring busy; with the lm_head tensor-parallel over the ring a
+    # token is finalised one slot after its last layer, so S + 1 sequences keep all S shards busy
+    NS = (world + (1 if tp_wanted else 0)) if args.in_flight <= 0 else args.in_flight
+    if args.split == "equal" or world == 1 or (tp_wanted and L % world == 0):
+        split = even_split(L, world)            # tensor-parallel head: every shard streams the same bytes with equal counts
     else:
         # contiguous slices balanced by the bytes a shard streams per token (the last shard also owns the
         # lm_head = 2.4 layers' worth): the assignment an operator posts to /v1/prepare_topology_manual
@@ -90,6 +93,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     ports = [base_port + 7 * r for r in range(world)]
     ts = TransportSettings()
     ts.hop_lanes = max(NS + 2, 4)
+    ts.head_tp = "on" if tp_wanted else "off"
     ts.sched_rounds_per_frame = args.sched_rounds
     ts.sched_frames_in_flight = args.sched_depth
     node = ShardNode(rank, ports[rank], transport_settings=ts, queue_size=256).start()
@@ -133,18 +137,24 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     def entries_done() -> int:
         return int(getattr(pol, "sched_entries_done", 0))
 
-    if last:
-        api = ApiNode(f"127.0.0.1:{ports[0]}", callback="local://")
-        mgr = api.manager
+    tp = bool(ad.head_tp)
+    api_rank = 0 if tp else world - 1          # tokens surface on the head shard with a tensor-parallel head, else on the tail
+    api_port = base_port + 7 * world + 3
+    cb = f"grpc://127.0.0.1:{api_port}" if tp else "local://"
+    on_api = rank == api_rank
+    if on_api:
+        api = ApiNode(f"127.0.0.1:{ports[0]}", callback="local://" if not tp else "grpc", grpc_port=api_port)
 
         def sink(msg):
             got.setdefault(msg.nonce, []).append((int(msg.token_id), float(msg.logprob)))
-        ad.token_sink = sink
+        ad.token_sink = sink                    # decode tokens: in-process, straight from the TokenTap
+        if tp:                                  # the tail's first tokens (prefill) arrive over gRPC SendToken
+            api.manager.resolve_request = lambda nonce, res: got.setdefault(nonce, []).append((int(res.token_id), float(res.logprob)))
 
         async def send_prompts():
             import numpy as np
             for n, nonce in enumerate(nonces):
-                await api.adapter.send_tokens(nonce, np.asarray(prompts[n], np.int32).tobytes(), "local://", logprobs=True,
+                await api.adapter.send_tokens(nonce, np.asarray(prompts[n], np.int32).tobytes(), cb, logprobs=True,
                                               decoding_config=types.SimpleNamespace(temperature=0.0, top_p=1.0, top_k=-1,
                                                                                     repetition_penalty=1.0, min_p=0.0,
                                                                                     min_tokens_to_keep=1))
@@ -156,7 +166,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     def lease_all(steps: int):
         async def go():
             for nonce in nonces:
-                await api.adapter.lease(nonce, steps, "local://")
+                await api.adapter.lease(nonce, steps, cb)
         api.call(go())
 
     def run_steps(steps: int, base_tokens: int, base_entries: int, timed: bool):
@@ -167,12 +177,15 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         barrier()
         e0.record(stream)
         t0 = time.perf_counter()
-        if last:
+        if on_api:
             lease_all(steps)
         _wait(lambda: entries_done() >= base_entries + steps * NS, 180, "schedule frames", poll=5e-5)
-        e1.record(stream)
         wall = None
-        if last:
+        if on_api and tp:      # head shard: its last kernels are the merges of the final tokens -> time through them
+            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=2e-5)
+            wall = time.perf_counter() - t0
+        e1.record(stream)
+        if on_api and not tp:
             _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=2e-5)
             wall = time.perf_counter() - t0
         stream.synchronize()
@@ -212,9 +225,9 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     launches_all = allsum(launches)
     step_err = int(allmax(float(step_err)))
     value = K * NS / ms * 1e3
-    check_token = int(allmax(float(got[nonces[0]][W + K][0]) if last else -1.0))
+    check_token = int(allmax(float(got[nonces[0]][W + K][0]) if on_api else -1.0))
     clocks = sampler.summary(tw0, tw1) if rank == 0 else None
-    tokens_ok = bool(allmax(0.0 if (not last or all(t >= 0 for n in nonces for t, _ in got[n])) else 1.0) == 0.0)
+    tokens_ok = bool(allmax(0.0 if (not on_api or all(t >= 0 for n in nonces for t, _ in got[n])) else 1.0) == 0.0)
 
     # ---- one sequence alone around the ring (latency view) + this rank's stand-alone step time
     K1 = min(K, 64)
@@ -226,12 +239,12 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         base_e = entries_done()
         base_t = len(got[nonces[0]])
         e2.record(stream)
-        if last:
-            api.call(api.adapter.lease(nonces[0], K1, "local://"))
+        if on_api:
+            api.call(api.adapter.lease(nonces[0], K1, cb))
         _wait(lambda: entries_done() >= base_e + K1, 120, "single-sequence schedule", poll=5e-5)
-        e3.record(stream)
-        if last:
+        if on_api:
             _wait(lambda: len(got[nonces[0]]) >= base_t + K1, 120, "single-sequence tokens")
+        e3.record(stream)
         stream.synchronize()
         barrier()
         single_ms = allmax(e2.elapsed_time(e3)) / K1
@@ -250,7 +263,10 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         peak, peak_src = peaks()
         tb = token_bytes(cfg)
         per_shard = [len(x) * layer_bytes(cfg) for x in split]
-        per_shard[-1] += 2 * cfg["vocab_size"] * H + 2 * H
+        if tp:
+            per_shard = [b + (2 * cfg["vocab_size"] * H) // world + 2 * H for b in per_shard]
+        else:
+            per_shard[-1] += 2 * cfg["vocab_size"] * H + 2 * H
         per_shard[0] += 2 * H
         slow = max(per_shard)
         if world == 1:
@@ -289,6 +305,8 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                        "l2": "inputs larger than L2 (>=1.7 GB of weights per shard step vs 126 MB L2); no flush",
                        "step_kernel": "k_shard_step via RingAdapter schedule (dn_shard_step_hop: wait + step + hop in one launch)",
                        "sequences_in_flight": NS, "hop": "CUDA-IPC peer stores + system-scope flag, fused into k_shard_step",
+                       "lm_head": (f"tensor-parallel over the {world} shards (vocab/{world} rows each; final hidden state broadcast + "
+                                   "partial (max, sum-exp, argmax) gather over NVLink inside k_shard_step)") if tp else "on the last shard",
                        "split": [f"{x[0]}-{x[-1]}" for x in split], "step_error": step_err,
                        "sched": {"rounds_per_frame": ts.sched_rounds_per_frame, "frames_in_flight": ts.sched_frames_in_flight}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,

@@ -52,6 +52,18 @@ class ModelCfg(C.Structure):
     ]
 
 
+class TpArgs(C.Structure):
+    """dn_tp_args (include/dnet_b200.h): tensor-parallel lm_head arguments of dn_shard_step_tp"""
+    _fields_ = [
+        ("hp_x", C.c_void_p), ("hp_wait_flag", C.c_void_p), ("hp_seq", C.c_uint32),
+        ("hp_dst", C.c_void_p), ("hp_dst_flag", C.c_void_p),
+        ("bc_n", C.c_int32), ("bc_dst", C.c_void_p * 16), ("bc_flag", C.c_void_p * 16), ("bc_seq", C.c_uint32),
+        ("mg_n", C.c_int32), ("mg_part", C.c_void_p), ("mg_flags", C.c_void_p), ("mg_seq", C.c_uint32),
+        ("mg_kv", C.c_void_p), ("mg_token_out", C.c_void_p), ("mg_logprob_out", C.c_void_p),
+        ("mg_slot", C.c_void_p), ("mg_slot_flag", C.c_void_p), ("mg_slot_seq", C.c_uint32),
+    ]
+
+
 def declared_symbols() -> List[str]:
     """Every function name include/dnet_b200.h declares (used by the export test)."""
     txt = HEADER_PATH.read_text()
@@ -89,6 +101,9 @@ _PROTOS = {
     "dn_window_forward": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _i, _vp, _vp]),
     "dn_shard_step": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "dn_shard_step_hop": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _u32, _vp, _vp, _vp, _u32, _vp]),
+    "dn_bind_head_slice": (_i, [_vp, _vp, _i, _i]),
+    "dn_shard_step_tp": (_i, [_vp, C.POINTER(C.c_int32), _i, _vp, _vp, _i, _i, _vp, _u32, _vp, _vp, _vp, _u32,
+                              C.POINTER(TpArgs), _vp]),
     "dn_step_error": (_i, [_vp, _vp]),
     "dn_step_error_clear": (_i, [_vp, _vp]),
     "dn_debug_scratch": (_i, [_vp, _i, _vp, _sz, _vp]),

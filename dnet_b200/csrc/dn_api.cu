@@ -144,7 +144,8 @@ struct dn_model {
   unsigned int* tickets = nullptr;       // [tmax * n_kv] attention + [1] head
   HeadPartial* head_part = nullptr;
   float* inv_freq = nullptr;
-  StepState* null_state = nullptr;
+  StepState* null_state = nullptr;      // zeroed step state + block table for launches without a nonce (head-part only)
+  int32_t* null_bt = nullptr;
   // paged KV pool: [local layer][page][2][n_kv][PAGE][HD]
   bf16* kv_pool = nullptr;
   size_t page_elems = 0, layer_elems = 0;
@@ -173,6 +174,9 @@ struct dn_model {
   int kvq_score_stride = 0;
   unsigned int* kvq_head_tk = nullptr;
   size_t kv_layer_bytes = 0;         // bytes of one local layer's pages (bf16 or packed)
+  // tensor-parallel lm_head: this shard's vocabulary slice (dn_bind_head_slice)
+  const bf16* head_slice = nullptr;
+  int head_row0 = 0, head_nrows = 0;
 };
 
 struct dn_kv {
@@ -379,6 +383,10 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   CK(cudaMalloc(&m->xb, (size_t)H * 2));
   CK(cudaMalloc(&m->mk_sync, 64));
   CK(util_fill0(m->mk_sync, 64));
+  CK(cudaMalloc(&m->null_state, sizeof(StepState)));
+  CK(util_fill0(m->null_state, sizeof(StepState)));
+  CK(cudaMalloc(&m->null_bt, 64));
+  CK(util_fill0(m->null_bt, 64));
   {
     const int qkvd = (cfg->n_heads + 2 * cfg->n_kv_heads) * HD;
     CK(cudaMalloc(&m->pf_xn, (size_t)TPF_MAX * H * 2));
@@ -409,6 +417,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   cudaFree(m->part); cudaFree(m->tickets); cudaFree(m->head_part); cudaFree(m->inv_freq); cudaFree(m->kv_pool);
   cudaFree(m->mk_bounds); cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
   cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
+  cudaFree(m->null_state); cudaFree(m->null_bt);
   cudaFree(m->kvq_stage); cudaFree(m->kvq_stage_bt); cudaFree(m->kvq_scores); cudaFree(m->kvq_head_tk);
   delete m;
   return DN_OK;
@@ -867,6 +876,7 @@ struct HopArgs {
   const uint32_t* wait_flag = nullptr; uint32_t wait_seq = 0;
   const int32_t* token_in = nullptr;
   void* send_dst = nullptr; uint32_t* send_flag = nullptr; uint32_t send_seq = 0;
+  const dn_tp_args* tp = nullptr;
 };
 static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
                            int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
@@ -899,10 +909,14 @@ extern "C" int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, 
 static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv,
                            int embed_from_token, int do_head, int32_t* token_out, float* logprob_out,
                            float* logits_f32_out, int advance, const HopArgs& hop, dn_stream s) {
-  if (!m || !x_inout || !kv || n < 0 || (n > 0 && !abs_layers)) return fail(DN_EINVAL, "bad argument");
-  if (kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
-  if (n == 0 && !do_head) return fail(DN_EINVAL, "nothing to do");
-  if (!g_capturing && kv->host_pos + 1 > kv->max_tokens) return fail(DN_ENOSPC, "KV capacity exceeded");
+  const dn_tp_args* tp = hop.tp;
+  const bool bubble = tp != nullptr && n == 0;          // tensor-parallel head: a launch that only serves another nonce's head part
+  if (!m || n < 0 || (n > 0 && !abs_layers)) return fail(DN_EINVAL, "bad argument");
+  if (!bubble && (!x_inout || !kv)) return fail(DN_EINVAL, "bad argument");
+  if (kv && kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
+  if (n == 0 && !do_head && !(tp && (tp->hp_x || tp->mg_n > 0))) return fail(DN_EINVAL, "nothing to do");
+  if (!g_capturing && n > 0 && kv->host_pos + 1 > kv->max_tokens) return fail(DN_ENOSPC, "KV capacity exceeded");
+  if (tp && tp->hp_x && (!m->head_slice || !m->norm)) return fail(DN_ENOENT, "tensor-parallel head part without a bound lm_head slice / final norm");
   int first_local = 0;
   for (int i = 0; i < n; ++i) {
     auto it = m->abs2local.find(abs_layers[i]);
@@ -924,7 +938,8 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.embed = embed_from_token ? m->embed : nullptr;
   p.xa = m->xa; p.xb = m->xb; p.hbuf = m->hbuf; p.qbuf = m->qbuf; p.attn = m->attn; p.act = m->act;
   p.x_out = (bf16*)x_inout;
-  p.block_table = kv->block_table; p.st = kv->st; p.inv_freq = m->inv_freq;
+  p.block_table = kv ? kv->block_table : m->null_bt; p.st = kv ? kv->st : m->null_state; p.inv_freq = m->inv_freq;
+  if (!kv && !m->null_state) return fail(DN_EINVAL, "no null step state");
   p.part = m->part; p.tickets = m->tickets;
   p.norm_w = m->norm; p.head_w = m->head; p.logits_bf16 = m->logits_bf16; p.logits_f32 = logits_f32_out;
   p.head_part = m->head_part; p.head_ticket = m->mk_sync + 3;
@@ -936,6 +951,21 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.inflight_hi = g_inflight_hi > g_inflight ? g_inflight_hi : g_inflight;
   // TMEM parking needs one fragment geometry (seg == 1024) in every phase
   p.park = (g_park && c.hidden % 1024 == 0 && c.ffn % 1024 == 0 && (c.n_heads * HD) % 1024 == 0) ? 1 : 0;
+  p.head_rows = c.vocab;
+  if (tp) {
+    if (tp->hp_x) {
+      p.hp_x = (const bf16*)tp->hp_x; p.hp_wait_flag = tp->hp_wait_flag; p.hp_seq = tp->hp_seq;
+      p.hp_row0 = m->head_row0; p.head_rows = m->head_nrows; p.head_w = m->head_slice;
+      p.hp_dst = (float*)tp->hp_dst; p.hp_dst_flag = tp->hp_dst_flag;
+      if (!p.hp_dst || !p.hp_dst_flag) return fail(DN_EINVAL, "head part without a destination");
+    }
+    if (tp->bc_n < 0 || tp->bc_n > 16 || tp->mg_n < 0 || tp->mg_n > 16) return fail(DN_EINVAL, "ring larger than 16 shards");
+    p.bc_n = tp->bc_n; p.bc_seq = tp->bc_seq;
+    for (int i = 0; i < tp->bc_n; ++i) { p.bc_dst[i] = (bf16*)tp->bc_dst[i]; p.bc_flag[i] = tp->bc_flag[i]; }
+    p.mg_n = tp->mg_n; p.mg_part = (const float*)tp->mg_part; p.mg_flags = tp->mg_flags; p.mg_seq = tp->mg_seq;
+    p.mg_st = tp->mg_kv ? tp->mg_kv->st : nullptr; p.mg_token_out = tp->mg_token_out; p.mg_logprob_out = tp->mg_logprob_out;
+    p.mg_slot = (int32_t*)tp->mg_slot; p.mg_slot_flag = tp->mg_slot_flag; p.mg_slot_seq = tp->mg_slot_seq;
+  }
   p.wait_flag = hop.wait_flag; p.wait_seq = hop.wait_seq; p.token_in = hop.token_in;
   p.send_dst = hop.send_dst; p.send_flag = hop.send_flag; p.send_seq = hop.send_seq;
   p.flags = g_mk_flags;
@@ -956,7 +986,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.sc_buf = m->kvq_scores;
   p.sc_stride = m->kvq_score_stride;
   p.head_tk = m->kvq_head_tk;
-  if (c.kv_bits && (!m->kvq_scores || m->kvq_score_stride < kv->max_tokens)) return fail(DN_EINVAL, "quantised KV: score scratch smaller than the nonce's capacity");
+  if (c.kv_bits && kv && (!m->kvq_scores || m->kvq_score_stride < kv->max_tokens)) return fail(DN_EINVAL, "quantised KV: score scratch smaller than the nonce's capacity");
   const int kmax = c.ffn > c.hidden ? c.ffn : c.hidden;
   int scratch = kmax * 2;
   const int attn_bytes = 8 * 132 * 4 + 64;                 // per-warp attention partials
@@ -997,8 +1027,34 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
     default: return fail(DN_EINVAL, "GQA group %d unsupported", m->G);
   }
   if (e != cudaSuccess) return fail(DN_ECUDA, "k_shard_step launch: %s", cudaGetErrorString(e));
-  if (advance && !g_capturing) kv->host_pos += 1;
+  if (advance && !g_capturing && kv) kv->host_pos += 1;
   return DN_OK;
+}
+
+// Tensor-parallel lm_head: bind this shard's vocabulary slice [row0, row0 + nrows) ([nrows, hidden] bf16, borrowed) --
+// the final norm comes through dn_bind_api as before.
+extern "C" int dn_bind_head_slice(dn_model* m, const void* slice, int row0, int nrows) {
+  if (!m || !slice || row0 < 0 || nrows <= 0 || row0 + nrows > m->cfg.vocab) return fail(DN_EINVAL, "bad head slice");
+  if (((uintptr_t)slice) & 15) return fail(DN_EINVAL, "head slice must be 16-byte aligned");
+  m->head_slice = static_cast<const bf16*>(slice);
+  m->head_row0 = row0; m->head_nrows = nrows;
+  return DN_OK;
+}
+
+// dn_shard_step_hop with the lm_head tensor-parallel over the ring (dn_tp_args): optional head part of another
+// nonce first, the layers, optional broadcast of the final hidden state (last shard), optional merge of the S
+// partials into a token (head shard).  n == 0 with kv == NULL is a launch that only serves head part / merge.
+extern "C" int dn_shard_step_tp(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv, int embed_from_token,
+                                int advance, const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
+                                void* send_dst, uint32_t* send_flag, uint32_t send_seq, const dn_tp_args* tp, dn_stream s) {
+  if (!tp) return fail(DN_EINVAL, "null tp args");
+  HopArgs h;
+  h.wait_flag = wait_flag; h.wait_seq = wait_seq; h.token_in = token_in;
+  h.send_dst = send_dst; h.send_flag = send_flag; h.send_seq = send_seq;
+  h.tp = tp;
+  if (send_dst && !send_flag) return fail(DN_EINVAL, "send_dst without send_flag");
+  return shard_step_impl(m, abs_layers, n, x_inout, kv, n > 0 ? embed_from_token : 0, 0, nullptr, nullptr, nullptr,
+                         n > 0 ? advance : 0, h, s);
 }
 
 // phase timestamps of the last dn_shard_step run with option mk_debug=1: [sm][layer][16] ns

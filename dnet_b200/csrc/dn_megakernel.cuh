@@ -104,6 +104,18 @@ struct MkParams {
   float* sc_buf;             // [n_heads][sc_stride] bf16-rounded scores of the current layer
   int sc_stride;
   unsigned int* head_tk;     // [n_heads] monotonic arrival counters: the splits of a head exchange (max, sum)
+  // ---- tensor-parallel lm_head over the ring (dn_shard_step_tp).  Every shard holds
+  //      vocab/S rows of the lm_head; the last shard broadcasts the final hidden state of a token to all
+  //      shards over NVLink, each computes (max, sum-exp, argmax) of its slice and stores that partial into the
+  //      head shard's table, which merges them -- so no shard streams the whole 1 GB head.
+  const bf16* hp_x;            // head part of THIS launch: final hidden state of the due nonce (local slot); null = none
+  const uint32_t* hp_wait_flag; uint32_t hp_seq;   // arrival flag of hp_x (released by the last shard's broadcast)
+  int hp_row0, head_rows;      // vocabulary rows of the local slice: [hp_row0, hp_row0 + head_rows) (head_w points at the slice)
+  float* hp_dst; uint32_t* hp_dst_flag;            // this shard's entry of the head shard's partial table + its flag
+  int bc_n; bf16* bc_dst[16]; uint32_t* bc_flag[16]; uint32_t bc_seq;   // last shard: where x_out is broadcast to
+  int mg_n; const float* mg_part; const uint32_t* mg_flags; uint32_t mg_seq;   // head shard: partial table [16][4], flags 64 B apart
+  StepState* mg_st; int32_t* mg_token_out; float* mg_logprob_out;
+  int32_t* mg_slot; uint32_t* mg_slot_flag; uint32_t mg_slot_seq;      // own lane slot: the token for the next step's token_in
 };
 
 // ---------------------------------------------------------------------------------
@@ -251,7 +263,7 @@ __device__ __forceinline__ MkPhase mk_phase(const MkParams& p, int ph) {
     case PH_O: d.K = p.n_heads * HD; d.nrows = p.H; d.align = 1; break;
     case PH_GU: d.K = p.H; d.nrows = 2 * p.FFN; d.align = 2; break;
     case PH_DOWN: d.K = p.FFN; d.nrows = p.H; d.align = 1; break;
-    default: d.K = p.H; d.nrows = p.vocab; d.align = 1; break;
+    default: d.K = p.H; d.nrows = p.head_rows; d.align = 1; break;
   }
   d.seg = (d.K % 1024 == 0) ? 1024 : ((d.K % 512 == 0) ? 512 : 256);
   return d;
@@ -340,6 +352,10 @@ __device__ __forceinline__ void mk_produce_phase(const MkParams& p, const MkLaye
 }
 __device__ __forceinline__ void mk_producer(const MkParams& p, MkRing& ring, int lane, int which) {
   unsigned int idx = 0;
+  if (p.hp_x != nullptr) {       // tensor-parallel head part runs FIRST (its input is another nonce's, already here)
+    const MkLayer L0 = p.layers[0];
+    mk_produce_phase(p, L0, PH_HEAD, ring, lane, which, idx, 0);
+  }
   for (int li = 0; li < p.n_layers; ++li) {
     const MkLayer L = p.layers[li];
     mk_produce_phase(p, L, PH_QKV, ring, lane, which, idx, li);
@@ -389,6 +405,10 @@ __device__ __forceinline__ void mk_prefetcher(const MkParams& p, int lane, volat
   unsigned int n = 0;
   bool alive = true;
   const unsigned int limit = (unsigned int)(p.pf_depth + p.n_stages);
+  if (p.hp_x != nullptr) {
+    const MkLayer L0 = p.layers[0];
+    mk_prefetch_phase(p, L0, PH_HEAD, lane, n, consumed, limit, alive);
+  }
   for (int li = 0; li < p.n_layers && alive; ++li) {
     const MkLayer L = p.layers[li];
     mk_prefetch_phase(p, L, PH_QKV, lane, n, consumed, limit, alive);
@@ -1056,6 +1076,82 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   float* red2 = red + 192;                                     // [2][MK_CW][MK_ROWS] row-block partial sums
   const unsigned int bar_base = *reinterpret_cast<volatile const unsigned int*>(p.bar_epoch);
   if (threadIdx.x == 0) bar_req[2] = bar_base;                 // red[59]: read by the poller after its first acquire of bar_req
+  if (p.hp_x != nullptr) {
+    // ===== tensor-parallel head part: (max, sum-exp, argmax) of this shard's vocabulary slice for the due nonce =====
+    if (threadIdx.x == 0 && p.hp_wait_flag != nullptr) {
+      uint32_t v;
+      const unsigned long long t0 = gtimer();
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.hp_wait_flag) : "memory");
+        if ((int32_t)(v - p.hp_seq) >= 0) break;
+        if (gtimer() - t0 > 5ull * MK_TIMEOUT_NS) { atomicExch(p.err, 4u); break; }
+      }
+      __threadfence();
+    }
+    cbar_sync();
+    mk_stage_rmsnorm(xs, red, p.hp_x, p.norm_w, p.H, p.eps);
+    float hm = -INFINITY, hl = 0.f;
+    int hi = 0x7fffffff;
+    mk_consume(p, PH_HEAD, 0, ring, xs, red2, cw, lane, consumed, cs, nblk, [&](int, bool) { return 0; },
+               [&](int vr, float v, bool owner, int) {
+      if (!owner) return;
+      const float lg = bf16r(v);
+      p.logits_bf16[p.hp_row0 + vr] = __float2bfloat16_rn(v);
+      const int gi = p.hp_row0 + vr;
+      if (lg > hm) { hl = hl * exp2f((hm - lg) * LOG2E) + 1.0f; hm = lg; hi = gi; }
+      else hl += exp2f((lg - hm) * LOG2E);
+    });
+    auto merge = [](float& m, float& l, int& idx, float om, float ol, int oi) {
+      const float nm = fmaxf(m, om);
+      const float a = (m == -INFINITY) ? 0.f : l * exp2f((m - nm) * LOG2E);
+      const float b = (om == -INFINITY) ? 0.f : ol * exp2f((om - nm) * LOG2E);
+      l = a + b;
+      if (om > m || (om == m && oi < idx)) idx = oi;
+      m = nm;
+    };
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, hm, s);
+      const float ol = __shfl_xor_sync(0xffffffffu, hl, s);
+      const int oi = __shfl_xor_sync(0xffffffffu, hi, s);
+      merge(hm, hl, hi, om, ol, oi);
+    }
+    int* redi = reinterpret_cast<int*>(red);
+    if (lane == 0) { red[cw] = hm; red[8 + cw] = hl; redi[16 + cw] = hi; }
+    cbar_sync();
+    if (threadIdx.x == 0) {
+      float m = red[0], l = red[8]; int idx = redi[16];
+      for (int w = 1; w < MK_CW; ++w) merge(m, l, idx, red[w], red[8 + w], redi[16 + w]);
+      HeadPartial hp; hp.m = m; hp.l = l; hp.idx = idx; hp.pad = 0;
+      p.head_part[blockIdx.x] = hp;
+      __threadfence();
+      const unsigned int old = atomicAdd(p.head_ticket, 1u);
+      redi[32] = (old == gridDim.x - 1) ? 1 : 0;
+    }
+    cbar_sync();
+    if (redi[32] && warp == 0) {
+      __threadfence();
+      float m = -INFINITY, l = 0.f; int idx = 0x7fffffff;
+      for (int i = lane; i < (int)gridDim.x; i += 32)
+        merge(m, l, idx, __ldcg(&p.head_part[i].m), __ldcg(&p.head_part[i].l), __ldcg(&p.head_part[i].idx));
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, s);
+        const float ol = __shfl_xor_sync(0xffffffffu, l, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, s);
+        merge(m, l, idx, om, ol, oi);
+      }
+      if (lane == 0) {
+        *p.head_ticket = 0u;
+        // this shard's partial -> the head shard's table (peer store over NVLink), then its flag
+        volatile float* d = p.hp_dst;
+        d[0] = m; d[1] = l; d[2] = __int_as_float(idx); d[3] = 0.f;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.hp_dst_flag), "r"(p.hp_seq) : "memory");
+      }
+    }
+    cbar_sync();
+  }
   if (p.wait_flag != nullptr) {
     // the weights of this step are already streaming into the ring while we wait for the hop
     if (threadIdx.x == 0) {
@@ -1286,6 +1382,51 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     cbar_sync();
     if (threadIdx.x == 0)
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.send_flag), "r"(p.send_seq) : "memory");
+  }
+  if (p.bc_n > 0 && p.n_layers > 0 && blockIdx.x == 0) {
+    // last shard, tensor-parallel head: broadcast the final hidden state to every shard's slot (itself included)
+    const uint4* src4 = reinterpret_cast<const uint4*>(p.x_out);
+    for (int d = 0; d < p.bc_n; ++d) {
+      uint4* dst4 = reinterpret_cast<uint4*>(p.bc_dst[d]);
+      for (int i = threadIdx.x; i < p.H / 8; i += MK_CTHREADS) dst4[i] = __ldcg(src4 + i);
+    }
+    __threadfence_system();
+    cbar_sync();
+    if (threadIdx.x < p.bc_n)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.bc_flag[threadIdx.x]), "r"(p.bc_seq) : "memory");
+  }
+  if (p.mg_n > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    // head shard: every shard's partial of the due nonce has landed (they ran their head parts while this launch
+    // computed its layers); merge in shard order -> token, logprob; hand the token to the next step (own lane slot)
+    float m = -INFINITY, l = 0.f; int idx = 0x7fffffff;
+    for (int i = 0; i < p.mg_n; ++i) {
+      uint32_t v;
+      const unsigned long long t0 = gtimer();
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.mg_flags + 16 * i) : "memory");
+        if ((int32_t)(v - p.mg_seq) >= 0) break;
+        if (gtimer() - t0 > 5ull * MK_TIMEOUT_NS) { atomicExch(p.err, 4u); break; }
+      }
+      const float om = __ldcg(p.mg_part + 4 * i), ol = __ldcg(p.mg_part + 4 * i + 1);
+      const int oi = __float_as_int(__ldcg(p.mg_part + 4 * i + 2));
+      const float nm = fmaxf(m, om);
+      const float a = (m == -INFINITY) ? 0.f : l * exp2f((m - nm) * LOG2E);
+      const float b = (om == -INFINITY) ? 0.f : ol * exp2f((om - nm) * LOG2E);
+      l = a + b;
+      if (om > m || (om == m && oi < idx)) idx = oi;
+      m = nm;
+    }
+    const float lse = bf16r(m + logf(l));
+    const float lp = bf16r(__fsub_rn(m, lse));
+    const unsigned int ecode = *reinterpret_cast<volatile unsigned int*>(p.err);
+    if (p.mg_st != nullptr) p.mg_st->token = idx;
+    if (p.mg_logprob_out != nullptr) *reinterpret_cast<volatile float*>(p.mg_logprob_out) = lp;
+    if (p.mg_slot != nullptr) *reinterpret_cast<volatile int32_t*>(p.mg_slot) = idx;
+    __threadfence_system();
+    if (p.mg_token_out != nullptr) *reinterpret_cast<volatile int32_t*>(p.mg_token_out) = ecode ? -(1000 + (int)ecode) : idx;
+    if (p.mg_slot_flag != nullptr)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.mg_slot_flag), "r"(p.mg_slot_seq) : "memory");
+    __threadfence_system();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (p.advance) p.st->pos = pos + 1;

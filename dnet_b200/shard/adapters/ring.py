@@ -106,6 +106,14 @@ class RingAdapter(TopologyAdapter):
         self._dseq: Dict[int, int] = {}                   # head: lane -> next decode-flag value to schedule
         self._sched_seq = 0
         self.stats = {"frames_hop": 0, "frames_bytes": 0, "frames_sched": 0, "tokens": 0}
+        # ring census (position / size) and the tensor-parallel lm_head it enables
+        self.head_tp_mode = str(getattr(self.transport_settings, "head_tp", "auto")).strip().lower()
+        self.ring_size = 1
+        self.ring_pos = 0
+        self.head_tp = False                  # lm_head split over the ring's shards during on-device decode
+        self._tp_flush = 0                    # head: bubble entries still owed so the last tokens' head parts run
+        self._sched_index = 0                 # head: ring-wide index of the next schedule entry
+        self._lane_last_idx: Dict[int, int] = {}
 
     # ------------------------------------------------------------------ reference surface
     @property
@@ -218,31 +226,54 @@ class RingAdapter(TopologyAdapter):
             if bind is not None:
                 bind()                      # this runs on the event-loop thread: bind it to the shard's device
             self._teardown_hop()
-            hop = HopLink(self.n_lanes, int(model.hidden_size), self.bulk_tokens)
+            layers = sorted(rt._assigned_set)
+            hop = HopLink(self.n_lanes, int(model.hidden_size), self.bulk_tokens, shard_id=rt.shard_id,
+                          first_layer=layers[0] if layers else -1, n_layers=len(layers))
             self._streams.configure_lanes(self.n_lanes)
             self._bulk_seq.clear()
             self._dseq.clear()
+            self._sched_index, self._tp_flush = 0, 0
+            self._lane_last_idx.clear()
             single = self.next_node is None
+            self.ring_size, self.ring_pos, self.head_tp = 1, 0, False
             if single:
                 hop.connect(None)
             else:
                 exchange = self.hop_exchange or self._grpc_hop_exchange
-                rt.hop_pending = hop              # lets the servicer answer the predecessor's b200.hop.open
-                ep = await exchange(hop.endpoint())
-                if ep is None:
+                rt.hop_pending = hop              # lets the servicer answer the predecessors' b200.hop.open
+                # ring census: ask for the endpoint k hops ahead until our own comes back
+                ring: list = []
+                for k in range(64):
+                    ep = await exchange(hop.endpoint(), k)
+                    if ep is None:
+                        break
+                    if self._ep_id(ep) == str(rt.shard_id):
+                        break
+                    ring.append(ep)
+                if not ring:
                     logger.warning("Shard %s: no hop endpoint from the next node; tensor bytes ride the gRPC stream",
                                    rt.shard_id)
                     hop.close()
                     rt.hop_pending = None
                     return
+                ep = ring[0]
                 if isinstance(ep, HopLink):      # the successor lives in this process: no IPC
                     hop.connect_local(ep)
                 else:
                     hop.connect(ep)
+                self._census(hop, ring)
             self.hop = hop
             rt.hop = hop
             rt.on_emit = self._device_egress
-            if self.is_tail or single:
+            rt.tp_head = None
+            if self.head_tp:
+                row0, row1 = await asyncio.get_running_loop().run_in_executor(rt.executor, rt.load_head_slice,
+                                                                               self.ring_pos, self.ring_size)
+                rt.tp_head = {"S": self.ring_size, "r": self.ring_pos, "rows": (row0, row1)}
+                logger.info("Shard %s: lm_head tensor-parallel over %d shards, this shard rows %d..%d", rt.shard_id,
+                            self.ring_size, row0, row1 - 1)
+            # tokens surface where they are finalised: the tail shard, or the head shard with a tensor-parallel head
+            if (self.is_tail and not self.head_tp) or single or (self.is_head and self.head_tp):
                 rt.token_tap = TokenTap(self.n_lanes, on_token=self._tap_token)
                 rt.token_tap.start()
             logger.info("Shard %s: device hop link up (%d lanes, head=%s tail=%s)", rt.shard_id, self.n_lanes,
@@ -270,19 +301,49 @@ class RingAdapter(TopologyAdapter):
             rt.hop = None
             rt.on_emit = None
 
-    async def _grpc_hop_exchange(self, own: dict) -> Optional[dict]:
+    @staticmethod
+    def _ep_id(ep) -> str:
+        return str(ep.shard_id if hasattr(ep, "shard_id") else ep.get("shard_id"))
+
+    def _census(self, hop, ring: list) -> None:
+        """``ring`` = endpoints of the successors in ring order (ours excluded).  Derive the ring size, our
+        position counted from the shard that owns layer 0, and -- when every shard runs one contiguous block and
+        the setting allows -- map every peer's head area (tensor-parallel lm_head)."""
+        from ..ring import HopLink
+
+        def first_layer(ep):
+            return int(ep.first_layer if isinstance(ep, HopLink) else ep.get("first_layer", -1))
+
+        order = ring + [hop]                                   # successors..., self
+        heads = [i for i, ep in enumerate(order) if first_layer(ep) == 0]
+        S = len(order)
+        if len(heads) != 1:
+            self.ring_size, self.ring_pos, self.head_tp = S, 0, False
+            return
+        h = heads[0]
+        order = order[h:] + order[:h]                          # ring positions 0..S-1
+        self.ring_size = S
+        self.ring_pos = next(i for i, ep in enumerate(order) if ep is hop)
+        want = self.head_tp_mode in ("on", "1", "true") or (self.head_tp_mode == "auto" and S >= 4)
+        ordered = all(first_layer(order[i]) < first_layer(order[i + 1]) for i in range(S - 1))
+        self.head_tp = bool(want and S >= 2 and S <= hop.mesh.MAX_SHARDS and ordered)
+        if self.head_tp:
+            hop.mesh.connect([None if ep is hop else (ep.mesh if isinstance(ep, HopLink) else ep["head"]) for ep in order],
+                             self.ring_pos)
+
+    async def _grpc_hop_exchange(self, own: dict, k: int = 0) -> Optional[dict]:
         """Ask the successor for its endpoint with a unary SendActivation whose dtype is ``b200.hop.open``;
         a dnet_b200 servicer answers with the endpoint as JSON in ``ActivationResponse.message``."""
         import json
 
         if self.next_node_stub is None:
             return None
-        req = pb2.ActivationRequest(nonce="", activation=pb2.Activation(data=b"", batch_size=0, shape=[], dtype="b200.hop.open",
+        req = pb2.ActivationRequest(nonce="", activation=pb2.Activation(data=b"", batch_size=0, shape=[int(k)], dtype="b200.hop.open",
                                                                       layer_id=-1),
                                     timestamp=utc_epoch_now(), node_origin=f"shard_{self.runtime.shard_id}", callback_url="")
         for _ in range(200):        # the successor may still be loading its model
             try:
-                resp = await self.next_node_stub.SendActivation(req, timeout=5.0)
+                resp = await self.next_node_stub.SendActivation(req, timeout=10.0)
                 if resp.success and resp.message.startswith("{"):
                     return json.loads(resp.message)
             except Exception as e:
@@ -374,22 +435,39 @@ class RingAdapter(TopologyAdapter):
 
     def _next_schedule(self) -> List[Tuple[int, int]]:
         """Up to ``rounds_per_frame`` rounds; one round = one decode step of every leased nonce, in lane
-        order.  The order is what every shard launches in, so it is decided exactly once, here."""
+        order.  The order is what every shard launches in, so it is decided exactly once, here.
+        With a tensor-parallel lm_head the token of entry j is finalised by the head shard at the END of its kernel
+        for entry j + S, so the same request's next step may be entry j + S + 1 at the
+        earliest: bubble entries are inserted wherever that distance would be violated, and S + 1 bubbles flush the
+        head parts of the last tokens once nothing is leased any more."""
         entries: List[Tuple[int, int]] = []
+        gap = self.ring_size + 1 if self.head_tp else 0
         for _ in range(self.rounds_per_frame):
             live = [(self._streams.lane_ctx(n), n) for n, left in self._leases.items() if left > 0]
             live = sorted(((c.lane, n, c) for c, n in live if c is not None and c.lane >= 0), key=lambda x: x[0])
             if not live:
                 break
             for lane, nonce, ctx in live:
+                if gap:
+                    short = gap - (self._sched_index - self._lane_last_idx.get(lane, -(1 << 30)))
+                    if short > 0:
+                        entries += [(fr.BUBBLE, 0)] * short
+                        self._sched_index += short
+                    self._lane_last_idx[lane] = self._sched_index
+                    self._tp_flush = gap
                 seq = self._dseq.get(lane, ctx.params.get("seq0", 1))
                 self._dseq[lane] = seq + 1
                 entries.append((lane, seq))
+                self._sched_index += 1
                 ctx.steps_enqueued += 1
                 self._streams.note_scheduled(ctx, seq + 1)
                 self._leases[nonce] -= 1
         for n in [n for n, left in self._leases.items() if left <= 0]:
             self._leases.pop(n, None)
+        if not entries and self._tp_flush:
+            entries = [(fr.BUBBLE, 0)] * self._tp_flush
+            self._sched_index += self._tp_flush
+            self._tp_flush = 0
         return entries
 
     async def _sched_worker(self):
@@ -397,7 +475,7 @@ class RingAdapter(TopologyAdapter):
         pending: Deque[Any] = deque()
         while self.running:
             try:
-                if not self._leases:
+                if not self._leases and not self._tp_flush:
                     self._lease_evt.clear()
                     await self._lease_evt.wait()
                 if not self.is_head:
@@ -621,9 +699,10 @@ class RingAdapter(TopologyAdapter):
         """Final-hop delivery of a sampled token to the API (transport only)."""
         self.stats["tokens"] += 1
         cb = msg.callback_url or ""
-        if cb.startswith("local://") or (not cb and self.token_sink is not None and not self.api_callback_address):
-            if self.token_sink is not None:
-                self.token_sink(msg)
+        if self.token_sink is not None:          # the API lives in this process: no RPC to ourselves
+            self.token_sink(msg)
+            return
+        if cb.startswith("local://"):
             return
         if cb:
             parsed = urlparse(cb)

@@ -24,6 +24,8 @@ HOP_PREFIX = "b200.hop/"
 SCHED_DTYPE = "b200.sched"
 LEASE_DTYPE = "b200.lease"
 
+BUBBLE = 0xFFFFFFFF            # schedule entry without a request: shards only serve due head parts (tensor-parallel lm_head)
+
 _HOP = struct.Struct("<4sIIII")      # magic, lane, seq (bulk arrival), seq0 (first decode seq), flags
 _LEASE = struct.Struct("<4sIIiI")    # magic, steps, has_token, token, lane_hint(unused)
 

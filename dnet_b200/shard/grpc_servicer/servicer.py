@@ -23,6 +23,16 @@ class GrpcServicer(DnetRingServiceServicer):
         try:
             if request.activation.dtype == "b200.hop.open":
                 rt = self.shard.runtime
+                hops = int(request.activation.shape[0]) if len(request.activation.shape) else 0
+                if hops > 0:      # ring census: relay the question `hops` shards further along the ring
+                    stub = getattr(self.shard.adapter, "next_node_stub", None)
+                    if stub is None:
+                        return pb2.ActivationResponse(success=False, message="no next node", node_id=str(self.shard.node_id))
+                    fwd = pb2.ActivationRequest()
+                    fwd.CopyFrom(request)
+                    del fwd.activation.shape[:]
+                    fwd.activation.shape.append(hops - 1)
+                    return await stub.SendActivation(fwd, timeout=10.0)
                 hop = getattr(rt, "hop", None) or getattr(rt, "hop_pending", None)
                 if hop is None:
                     return pb2.ActivationResponse(success=False, message="no hop lanes on this shard (yet)",

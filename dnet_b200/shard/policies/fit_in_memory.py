@@ -31,6 +31,10 @@ class FitInMemoryPolicy(ComputePolicy):
         self._mode = "fit"
         self._run_arrays = {}            # tuple(run) -> ctypes int32 array handed to dn_shard_step
         self.sched_entries_done = 0      # decode steps launched from schedule frames (progress signal for drivers)
+        from collections import deque
+        self._tp_hist = deque()          # tensor-parallel head: recent schedule entries (None = bubble) ...
+        self._tp_hist_base = 0           # ... the ring-wide index of hist[0] ...
+        self._tp_index = 0               # ... and of the next entry
         local_count = max(1, len(self.runtime.assigned_layers))
         requested_w = max(1, int(req.window_size))
         self.window_size = min(local_count, requested_w)
@@ -126,6 +130,9 @@ class FitInMemoryPolicy(ComputePolicy):
                     arr = self._run_arrays[key] = (C.c_int32 * len(run))(*run)
                 s = rt.compute_stream_ptr
                 now = None
+                if getattr(rt, "tp_head", None):
+                    self._launch_sched_tp(msg.sched, run, arr, first, last)
+                    return
                 for lane, seq in msg.sched:
                     nonce = rt.lane_nonce.get(lane)
                     ns = rt._kv_by_nonce.get(nonce) if nonce is not None else None
@@ -159,6 +166,74 @@ class FitInMemoryPolicy(ComputePolicy):
                 except Exception:
                     ev = None
                 ticket.record(ev)
+
+    def _launch_sched_tp(self, entries, run, arr, first: bool, last: bool) -> None:
+        """Schedule entries with the lm_head tensor-parallel over the ring.
+
+        Entry i of the ring-wide schedule makes shard r (of S) launch ONE kernel that
+          * first serves the head part of the request of entry i - (S - r): by then the last shard has broadcast
+            that request's final hidden state to every shard (it ran entry i - (S - r) one kernel earlier in
+            wall-clock terms -- the pipeline skew), so all shards compute their vocabulary slices in the same
+            slot and store the partial (max, sum-exp, argmax) into the head shard's table;
+          * then runs its layers for entry i's own request (nothing for a bubble entry);
+          * on the last shard, broadcasts the resulting final hidden state;
+          * on the head shard, finally merges the S partials of the head part it started with into the token,
+            hands it to the request's next step (own lane slot + flag) and to the host (TokenTap).
+        The history of entries is all a shard needs; it is identical on every shard because the schedule is."""
+        import time
+
+        rt = self.runtime
+        hop, mesh = rt.hop, rt.hop.mesh
+        lib = _cabi.load()
+        S, r = int(rt.tp_head["S"]), int(rt.tp_head["r"])
+        hist = self._tp_hist
+        s = rt.compute_stream_ptr
+        now = time.perf_counter()
+        for lane, seq in entries:
+            real = lane != fr.BUBBLE
+            idx = self._tp_index
+            self._tp_index += 1
+            hist.append((lane, seq) if real else None)
+            if len(hist) > 64:
+                hist.popleft()
+                self._tp_hist_base += 1
+            j = idx - (S - r) - self._tp_hist_base
+            due = hist[j] if 0 <= j < len(hist) else None
+            tp = _cabi.TpArgs()
+            if due is not None:
+                dl, dq = due
+                head_d, head_f = mesh.peers[0]
+                tp.hp_x, tp.hp_wait_flag, tp.hp_seq = mesh.x_slot(dl), mesh.x_flag(dl), dq
+                tp.hp_dst, tp.hp_dst_flag = mesh.partial(dl, r, head_d), mesh.p_flag(dl, r, head_f)
+                if r == 0:
+                    dn = rt.lane_nonce.get(dl)
+                    dns = rt._kv_by_nonce.get(dn) if dn is not None else None
+                    tp.mg_n, tp.mg_part, tp.mg_flags, tp.mg_seq = S, mesh.partial(dl, 0), mesh.p_flag(dl, 0), dq
+                    if dns is not None:
+                        tok_ptr, lp_ptr = rt.token_tap.post(dl, (dn, dq, dns.params))
+                        tp.mg_kv, tp.mg_token_out, tp.mg_logprob_out = dns.kv._h, tok_ptr, lp_ptr
+                    tp.mg_slot, tp.mg_slot_flag, tp.mg_slot_seq = hop.rx.slot(dl), hop.rx.flag(dl), dq + 1
+            if not real:
+                if due is not None:
+                    _cabi.check(lib.dn_shard_step_tp(rt.model._h, None, 0, None, None, 0, 0, None, 0, None, None, None, 0,
+                                                     C.byref(tp), s))
+                continue
+            nonce = rt.lane_nonce.get(lane)
+            ns = rt._kv_by_nonce.get(nonce) if nonce is not None else None
+            if ns is None:
+                logger.error("schedule entry for lane %d: no request holds that lane on shard %s", lane, rt.shard_id)
+                continue
+            if last:
+                tp.bc_n, tp.bc_seq = S, seq
+                for d in range(S):
+                    pd, pf = mesh.peers[d]
+                    tp.bc_dst[d], tp.bc_flag[d] = mesh.x_slot(lane, pd), mesh.x_flag(lane, pf)
+            _cabi.check(lib.dn_shard_step_tp(
+                rt.model._h, arr, len(run), ns.x1.data_ptr() if first else hop.rx.slot(lane), ns.kv._h, 1 if first else 0, 1,
+                hop.rx.flag(lane), seq, hop.rx.slot(lane) if first else None,
+                None if last else hop.tx_slot(lane), None if last else hop.tx_flag(lane), seq, C.byref(tp), s))
+            rt._kv_last_seen[nonce] = now
+            self.sched_entries_done += 1
 
     def _process_seed(self, msg: ActivationMessage) -> None:
         """A seeded ``b200.lease``: put ``msg.token_id`` into the head shard's own lane slot and publish

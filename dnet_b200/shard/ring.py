@@ -149,17 +149,22 @@ class HopLink:
     successor and no IPC is involved.
     """
 
-    def __init__(self, n_lanes: int, hidden: int, bulk_tokens: int = 512):
+    def __init__(self, n_lanes: int, hidden: int, bulk_tokens: int = 512, shard_id=None, first_layer: int = -1,
+                 n_layers: int = 0):
         self.n_lanes, self.hidden, self.bulk_tokens = int(n_lanes), int(hidden), int(bulk_tokens)
+        self.shard_id, self.first_layer, self.n_local_layers = shard_id, int(first_layer), int(n_layers)
         self.rx = HopReceiver(self.n_lanes, hidden * 2)
         self.rx_bulk = HopReceiver(self.n_lanes, self.bulk_tokens * hidden * 2)
+        self.mesh = HeadMesh(self.n_lanes, hidden)     # tensor-parallel lm_head area (used when the ring enables it)
         self.tx: Optional[HopSender] = None
         self.tx_bulk: Optional[HopSender] = None
 
     def endpoint(self) -> dict:
         a, b = self.rx.endpoint(), self.rx_bulk.endpoint()
         return {"n_lanes": self.n_lanes, "hidden": self.hidden, "bulk_tokens": self.bulk_tokens,
-                "decode": [a.data_handle.hex(), a.flag_handle.hex()], "bulk": [b.data_handle.hex(), b.flag_handle.hex()]}
+                "shard_id": str(self.shard_id), "first_layer": self.first_layer, "n_layers": self.n_local_layers,
+                "decode": [a.data_handle.hex(), a.flag_handle.hex()], "bulk": [b.data_handle.hex(), b.flag_handle.hex()],
+                "head": self.mesh.endpoint()}
 
     def connect(self, ep: Optional[dict]) -> None:
         """ep=None: self-loop (single shard, or a successor living in this process passes its HopLink)."""
@@ -198,7 +203,75 @@ class HopLink:
             if t is not None:
                 t.close()
         self.tx = self.tx_bulk = None
+        self.mesh.close()
         _PARKED_RECEIVERS.extend((self.rx, self.rx_bulk))
+
+
+class HeadMesh:
+    """Tensor-parallel lm_head over the ring: this shard's receive area + every peer's area mapped.
+
+    Per lane the area holds the final hidden state of the lane's token (written by the LAST shard's
+    broadcast, one arrival flag) and -- used on the HEAD shard only -- a table of up to 16 partial
+    results (max, sum-exp, argmax, pad: 16 bytes each; one flag per shard).  Flag values are the
+    lane's decode sequence numbers, so they only grow."""
+
+    MAX_SHARDS = 16
+
+    def __init__(self, n_lanes: int, hidden: int):
+        self.lib = _cabi.load()
+        self.n_lanes, self.hidden = int(n_lanes), int(hidden)
+        self.slot_bytes = hidden * 2 + self.MAX_SHARDS * 16
+        d, f = C.c_void_p(), C.c_void_p()
+        _cabi.check(self.lib.dn_hop_alloc(self.n_lanes * self.slot_bytes, C.byref(d)))
+        _cabi.check(self.lib.dn_hop_alloc(self.n_lanes * (1 + self.MAX_SHARDS) * 64, C.byref(f)))
+        self.data_ptr, self.flag_ptr = d.value, f.value
+        self.peers: List[Tuple[int, int]] = []        # ring position -> (data_ptr, flag_ptr) in THIS process
+        self._imported: List[int] = []
+
+    # -- addresses inside an area (ours or a peer's) ---------------------------------------------
+    def x_slot(self, lane: int, base: Optional[int] = None) -> int:
+        return (self.data_ptr if base is None else base) + lane * self.slot_bytes
+
+    def partial(self, lane: int, shard: int, base: Optional[int] = None) -> int:
+        return self.x_slot(lane, base) + self.hidden * 2 + shard * 16
+
+    def x_flag(self, lane: int, fbase: Optional[int] = None) -> int:
+        return (self.flag_ptr if fbase is None else fbase) + lane * (1 + self.MAX_SHARDS) * 64
+
+    def p_flag(self, lane: int, shard: int, fbase: Optional[int] = None) -> int:
+        return self.x_flag(lane, fbase) + (1 + shard) * 64
+
+    # -- exchange ----------------------------------------------------------------------------------
+    def endpoint(self) -> list:
+        hd, hf = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+        _cabi.check(self.lib.dn_hop_export(self.data_ptr, hd))
+        _cabi.check(self.lib.dn_hop_export(self.flag_ptr, hf))
+        return [bytes(hd).hex(), bytes(hf).hex()]
+
+    def connect(self, ring: list, own_position: int) -> None:
+        """``ring``: per ring position either this process's HeadMesh (same process), ``None`` at
+        ``own_position``, or the peer's endpoint [data_handle_hex, flag_handle_hex]."""
+        self.peers = []
+        for pos, ep in enumerate(ring):
+            if pos == own_position or ep is None:
+                self.peers.append((self.data_ptr, self.flag_ptr))
+            elif isinstance(ep, HeadMesh):
+                self.peers.append((ep.data_ptr, ep.flag_ptr))
+            else:
+                d, f = C.c_void_p(), C.c_void_p()
+                hd = (C.c_uint8 * 64).from_buffer_copy(bytes.fromhex(ep[0]))
+                hf = (C.c_uint8 * 64).from_buffer_copy(bytes.fromhex(ep[1]))
+                _cabi.check(self.lib.dn_hop_import(hd, C.byref(d)))
+                _cabi.check(self.lib.dn_hop_import(hf, C.byref(f)))
+                self.peers.append((d.value, f.value))
+                self._imported += [d.value, f.value]
+
+    def close(self) -> None:
+        for ptr in self._imported:
+            self.lib.dn_hop_close(ptr)
+        self._imported = []
+        self.peers = []
+        _PARKED_RECEIVERS.append(self)      # exported memory: parked, not freed (see HopLink.close)
 
 
 def even_split(num_layers: int, world: int) -> List[List[int]]:

@@ -293,13 +293,7 @@ class ShardRuntime:
         tied = bool(self.model_metadata.model_config.get("tie_word_embeddings", False))
         api: Dict[str, torch.Tensor] = {}
 
-        def _dev(info):
-            src = self.model_metadata.source
-            if isinstance(src, SyntheticSource):
-                t = torch.empty(tuple(info.shape), dtype=torch.bfloat16, device="cuda")
-                src.fill_device(info, t)
-                return t
-            return load_weight(info, {}, src).to("cuda", non_blocking=False).contiguous()
+        _dev = self._api_tensor_to_device
 
         if has_start or (has_end and tied):
             api["embed_tokens.weight"] = _dev(self.model_metadata.embed_tokens["weight"])
@@ -314,6 +308,45 @@ class ShardRuntime:
         if api:
             self.model.load_weights(list(api.items()), strict=False)
         torch.cuda.synchronize()   # loads ran on torch's current stream; compute runs on compute_stream
+
+    def _api_tensor_to_device(self, info) -> torch.Tensor:
+        src = self.model_metadata.source
+        if isinstance(src, SyntheticSource):
+            t = torch.empty(tuple(info.shape), dtype=torch.bfloat16, device="cuda")
+            src.fill_device(info, t)
+            return t
+        return load_weight(info, {}, src).to("cuda", non_blocking=False).contiguous()
+
+    def load_head_slice(self, position: int, ring_size: int) -> tuple:
+        """Tensor-parallel lm_head over the ring: bind this shard's vocabulary rows
+        [V*position/S, V*(position+1)/S) and the final norm (every shard applies it to the hidden state the
+        last shard broadcasts).  The shard that owns the last layer keeps the full head (prefill samples with
+        it) and its slice is a view into it; the others load only their rows."""
+        self._bind_thread_device()
+        md = self.model_metadata
+        V = int(self.model.vocab_size)
+        row0, row1 = V * position // ring_size, V * (position + 1) // ring_size
+        tied = bool(md.model_config.get("tie_word_embeddings", False))
+        with self._model_lock:
+            api = self._api_tensors
+            full = api.get("lm_head.weight") if not tied else api.get("embed_tokens.weight")
+            if "norm.weight" not in api:
+                api["norm.weight"] = self._api_tensor_to_device(md.norm["weight"])
+            if full is None:
+                info = (md.embed_tokens if tied else md.lm_head)["weight"]
+                whole = self._api_tensor_to_device(info)          # temporary: only the slice is kept
+                if whole.shape[0] != V and whole.shape[1] == V:
+                    whole = whole.t().contiguous()
+                sl = whole[row0:row1].clone()
+                del whole
+                torch.cuda.empty_cache()
+            else:
+                sl = full[row0:row1]
+            api["_head_slice"] = sl
+            self.model.load_weights([(k, v) for k, v in api.items() if not k.startswith("_")], strict=False)
+            _cabi.check(_cabi.load().dn_bind_head_slice(self.model._h, sl.data_ptr(), row0, row1 - row0))
+            torch.cuda.synchronize()
+        return row0, row1
 
     def unload_model_core(self) -> ShardUnloadModelResponse:
         try:

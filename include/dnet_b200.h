@@ -147,6 +147,36 @@ int dn_shard_step_hop(dn_model* m, const int32_t* abs_layers, int n, void* x_ino
                       int embed_from_token, int do_head, int32_t* token_out, float* logprob_out, int advance,
                       const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
                       void* send_dst, uint32_t* send_flag, uint32_t send_seq, dn_stream s);
+/* ---- tensor-parallel lm_head over the ring: every shard holds vocab/S rows of the head (dn_bind_head_slice); the
+ *      last shard broadcasts a token's final hidden state to every shard over NVLink, each computes (max, sum-exp,
+ *      argmax) of its slice and stores it into the head shard's table, which merges the S partials into the token.
+ *      Replaces normalize + lm_project + Sampler.sample(temperature 0) on the end shard (fit_in_memory.py:134-157)
+ *      for the on-device decode schedule; all pointers except hp_x / mg_part / mg_flags may be peer (IPC) memory. */
+typedef struct dn_tp_args {
+  const void* hp_x;                 /* head part of THIS launch: [hidden] bf16 final hidden state, local; NULL = none */
+  const uint32_t* hp_wait_flag;     /* its arrival flag (>= hp_seq) */
+  uint32_t hp_seq;
+  void* hp_dst;                     /* 4 floats (m, l, idx bits, pad): this shard's entry of the head shard's table */
+  uint32_t* hp_dst_flag;            /* released with hp_seq */
+  int32_t bc_n;                     /* last shard: number of destinations of the final hidden state (ring size) */
+  void* bc_dst[16];
+  uint32_t* bc_flag[16];
+  uint32_t bc_seq;
+  int32_t mg_n;                     /* head shard: number of partials to merge at the end of the launch (ring size) */
+  const void* mg_part;              /* [16][4] floats, local */
+  const uint32_t* mg_flags;         /* one flag per 64 bytes, local */
+  uint32_t mg_seq;
+  dn_kv* mg_kv;                     /* the due nonce's step state receives the token */
+  int32_t* mg_token_out;            /* host-visible (pinned) token / logprob, as dn_shard_step */
+  float* mg_logprob_out;
+  void* mg_slot;                    /* own lane slot: token for the nonce's next step (token_in) ... */
+  uint32_t* mg_slot_flag;           /* ... and its flag, released with mg_slot_seq */
+  uint32_t mg_slot_seq;
+} dn_tp_args;
+int dn_bind_head_slice(dn_model* m, const void* slice /* [nrows, hidden] bf16 */, int row0, int nrows);
+int dn_shard_step_tp(dn_model* m, const int32_t* abs_layers, int n, void* x_inout, dn_kv* kv, int embed_from_token,
+                     int advance, const uint32_t* wait_flag, uint32_t wait_seq, const int32_t* token_in,
+                     void* send_dst, uint32_t* send_flag, uint32_t send_seq, const dn_tp_args* tp, dn_stream s);
 int dn_step_error(dn_model* m, dn_stream s);
 /* 0, or the code of a timed-out bounded wait inside k_shard_step (2 ring, 3 grid barrier, 4 hop flag).  The word is
  * sticky and the kernel reports it to the host as token_out = -(1000 + code); dn_step_error_clear resets it

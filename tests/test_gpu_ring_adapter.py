@@ -122,17 +122,18 @@ def test_two_shards_one_process_activations_travel_as_device_hops(tiny):
     api = None
     try:
         # in-process hop exchange: each adapter is handed its successor's HopLink object (no CUDA IPC)
-        def exchange_for(peer):
-            async def ex(own):
+        def exchange_for(me, peer):
+            async def ex(own, k=0):          # the ring census asks for the endpoint k hops ahead
+                node = peer if k % 2 == 0 else me
                 for _ in range(600):
-                    hop = peer.runtime.hop or peer.runtime.hop_pending
+                    hop = node.runtime.hop or node.runtime.hop_pending
                     if hop is not None:
                         return hop
                     await asyncio.sleep(0.05)
                 return None
             return ex
-        n0.adapter.hop_exchange = exchange_for(n1)
-        n1.adapter.hop_exchange = exchange_for(n0)
+        n0.adapter.hop_exchange = exchange_for(n0, n1)
+        n1.adapter.hop_exchange = exchange_for(n1, n0)
         import concurrent.futures as cf
         with cf.ThreadPoolExecutor(2) as ex:
             f0, f1 = ex.submit(n0.load_model, r0), ex.submit(n1.load_model, r1)

@@ -569,3 +569,41 @@ def test_shard_admit_frame_and_load_unload():
         assert not rt.started and not ad.running
 
     asyncio.run(main())
+
+
+# ---------------------------------------------------------------------------- tensor-parallel lm_head schedule
+def test_tp_head_schedule_keeps_a_requests_steps_S_plus_1_entries_apart_and_flushes(grpc_ok):
+    """With the lm_head tensor-parallel over an S-shard ring the token of entry j exists after entry j + S, so the
+    head shard may schedule the same request again at entry j + S + 1 at the earliest: bubbles fill the gap when
+    fewer than S + 1 requests are leased, none are needed with S + 1 or more, and S + 1 trailing bubbles let the
+    last tokens' head parts run."""
+    S = 4
+    for n_req, steps in ((1, 3), (2, 4), (5, 3), (7, 2)):
+        ad, rt = make_adapter(assigned_next={0})
+        rt._assigned_set = {0}
+        ad.total_layers, ad.ring_size, ad.head_tp, ad.rounds_per_frame = 8, S, True, 3
+        ad._streams.configure_lanes(8)
+        for i in range(n_req):
+            ad._streams.claim_lane(f"r{i}").params["seq0"] = 1
+            ad._leases[f"r{i}"] = steps
+        stream = []
+        while True:
+            e = ad._next_schedule()
+            if not e:
+                break
+            stream += e
+        real = [(i, lane, seq) for i, (lane, seq) in enumerate(stream) if lane != fr.BUBBLE]
+        assert len(real) == n_req * steps
+        last = {}
+        for i, lane, seq in real:
+            if lane in last:
+                assert i - last[lane][0] >= S + 1, f"lane {lane}: entries {last[lane][0]} and {i} too close ({n_req} requests)"
+                assert seq == last[lane][1] + 1
+            last[lane] = (i, seq)
+        bubbles = sum(1 for lane, _ in stream if lane == fr.BUBBLE)
+        if n_req >= S + 1:
+            assert bubbles == S + 1, "a full ring needs no padding, only the final flush"
+        assert all(lane == fr.BUBBLE for lane, _ in stream[-(S + 1):])          # the flush
+        # every real entry's token is merged by the head at entry j + S, which exists in the stream
+        assert all(i + S < len(stream) for i, _, _ in real)
+        assert fr.unpack_sched(fr.pack_sched(stream)) == stream                 # bubbles survive the wire format
