@@ -384,6 +384,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     _cabi.init(local_rank)
     import bench as _b                     # bench_ring imports `bench`; this file runs as __main__
     _b._REAL_STDOUT, _b.PROMPT_LEN = _REAL_STDOUT, PROMPT_LEN
+    if args.config == "swap":
+        from bench_swap import run_swap
+        return run_swap(args, rank, local_rank, world)
     from bench_ring import run_ring
     return run_ring(args, rank, local_rank, world)
 
@@ -432,6 +435,10 @@ def main():
                     help="N>1: lm_head tensor-parallel over the ring's shards (auto: rings of >= 4 shards)")
     ap.add_argument("--sched-rounds", type=int, default=8, help="decode rounds per schedule frame (head shard's RingAdapter)")
     ap.add_argument("--sched-depth", type=int, default=4, help="schedule frames in flight")
+    ap.add_argument("--config", default="decode", choices=["decode", "swap"],
+                    help="decode: BASELINE configs[1] (the bench contract); swap: configs[3], Llama-3-70B layer swap (bench_swap.py)")
+    ap.add_argument("--swap-window", type=int, default=4, help="--config swap: window_size = residency_size (HBM layer slots per window)")
+    ap.add_argument("--swap-resident-windows", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

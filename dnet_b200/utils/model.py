@@ -169,10 +169,14 @@ class SyntheticSource:
     ``host_tensor`` is unavailable: tensors are materialised straight into HBM slots.
     """
 
-    def __init__(self, config: dict, seed: int = 0, std: float = 0.02, layers=None):
+    def __init__(self, config: dict, seed: int = 0, std: float = 0.02, layers=None, share_layers: bool = False):
         self.config = config
         self.seed = seed
         self.std = std
+        # share_layers: every layer gets the values of the first one (host copies are generated once per tensor kind);
+        # for benchmarks of data movement at sizes where generating 70B distinct parameters would dominate the run
+        self.share_layers = bool(share_layers)
+        self._host_cache: Dict[str, torch.Tensor] = {}
         c = config
         H, F_, V = c["hidden_size"], c["intermediate_size"], c["vocab_size"]
         hd = c.get("head_dim") or H // c["num_attention_heads"]
@@ -221,10 +225,17 @@ class SyntheticSource:
             flat[i:i + n] = (torch.randn(n, generator=g, device=dst.device, dtype=torch.float32) * std).to(dst.dtype)
 
     def host_tensor(self, info: TensorInfo) -> torch.Tensor:
+        name = info.filename[len("syn://"):]
+        key = name.split(".", 3)[3] if (self.share_layers and name.startswith("model.layers.")) else None
+        if key is not None and key in self._host_cache:
+            return self._host_cache[key]
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         t = torch.empty(info.shape, dtype=torch.bfloat16, device=dev)
         self.fill_device(info, t)
-        return t.cpu()
+        t = t.cpu()
+        if key is not None:
+            self._host_cache[key] = t
+        return t
 
 
 # ---------------------------------------------------------------------------------
