@@ -179,14 +179,14 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         t0 = time.perf_counter()
         if on_api:
             lease_all(steps)
-        _wait(lambda: entries_done() >= base_entries + steps * NS, 180, "schedule frames", poll=5e-5)
+        _wait(lambda: entries_done() >= base_entries + steps * NS, 180, "schedule frames", poll=2e-4)
         wall = None
         if on_api and tp:      # head shard: its last kernels are the merges of the final tokens -> time through them
-            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=2e-5)
+            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=1e-4)
             wall = time.perf_counter() - t0
         e1.record(stream)
         if on_api and not tp:
-            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=2e-5)
+            _wait(lambda: all(len(got[n]) >= base_tokens + steps for n in nonces), 180, "tokens", poll=1e-4)
             wall = time.perf_counter() - t0
         stream.synchronize()
         torch.cuda.synchronize()
@@ -200,8 +200,10 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         sampler.start()
         time.sleep(0.3)
     l0 = lib.dn_launch_count()
+    h0, n0 = pol.sched_host_s, pol.sched_host_entries
     tw0 = time.perf_counter()
     ms_local, wall = run_steps(K, 1 + W, W * NS, True)
+    host_us = (pol.sched_host_s - h0) / max(1, pol.sched_host_entries - n0) * 1e6
     tw1 = time.perf_counter()
     launches = int(lib.dn_launch_count() - l0)
     step_err = int(lib.dn_step_error(rt.model._h, rt.compute_stream_ptr))
@@ -221,6 +223,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         return int(t.item())
 
     ms = allmax(ms_local)
+    host_us_max = allmax(host_us)
     e2e_s = allmax(wall if wall is not None else 0.0)
     launches_all = allsum(launches)
     step_err = int(allmax(float(step_err)))
@@ -241,7 +244,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         e2.record(stream)
         if on_api:
             api.call(api.adapter.lease(nonces[0], K1, cb))
-        _wait(lambda: entries_done() >= base_e + K1, 120, "single-sequence schedule", poll=5e-5)
+        _wait(lambda: entries_done() >= base_e + K1, 120, "single-sequence schedule", poll=2e-4)
         if on_api:
             _wait(lambda: len(got[nonces[0]]) >= base_t + K1, 120, "single-sequence tokens")
         e3.record(stream)
@@ -308,7 +311,8 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                        "lm_head": (f"tensor-parallel over the {world} shards (vocab/{world} rows each; final hidden state broadcast + "
                                    "partial (max, sum-exp, argmax) gather over NVLink inside k_shard_step)") if tp else "on the last shard",
                        "split": [f"{x[0]}-{x[-1]}" for x in split], "step_error": step_err,
-                       "sched": {"rounds_per_frame": ts.sched_rounds_per_frame, "frames_in_flight": ts.sched_frames_in_flight}},
+                       "sched": {"rounds_per_frame": ts.sched_rounds_per_frame, "frames_in_flight": ts.sched_frames_in_flight,
+                                 "host_us_per_entry_max_rank": host_us_max}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
             "ring_hop_us": hop,
             "check": {"nonce0_token_after_steps": W + K, "token": check_token, "all_tokens_valid": tokens_ok,

@@ -45,6 +45,8 @@ static int g_inflight_hi = 3;   // step kernel: cap while the consumers are star
 static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
 static int g_inflight = 2;      // step kernel: ring stages with loads outstanding while the consumers are not starving (barriers, staging); measured caps 2/3/4/5/none = 357/381/374/369/366 tok/s static, 2-when-idle/3-when-starving +0.7 % on top
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
+static int g_attn_tc = 1;       // step kernel: tensor-core attention phase (shared-memory K/V tiles + mma) for long contexts ...
+static int g_attn_tc_min = 1024;   // ... from this many tokens of context on (bf16 KV)
 static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
                               // harmful beyond -- 148 SMs x depth x 32 KB must stay well inside one L2 partition)
@@ -283,6 +285,8 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "gemm_bn256")) { g_gemm_bn256 = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "tc_attn")) { g_tc_attn = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "attn_tc")) { g_attn_tc = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "attn_tc_min")) { g_attn_tc_min = (int)value; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
   if (!strcmp(key, "inflight_hi")) { g_inflight_hi = value < 0 ? 0 : (int)value; return DN_OK; }
   if (!strcmp(key, "park")) { g_park = value != 0; return DN_OK; }
@@ -993,6 +997,9 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   if (scratch < attn_bytes) scratch = attn_bytes;
   const int merge_bytes = c.n_heads * HD * 2 + c.n_heads * m->nsplit * 8 + 64;   // o_proj vector + (m,l) table
   if (scratch < merge_bytes) scratch = merge_bytes;
+  // long contexts: attention on the tensor cores, its per-warp K/V tiles alias the activation scratch (one ring stage less)
+  p.attn_tc = (g_attn_tc && c.kv_bits == 0 && kv && n > 0 && kv->host_pos + 1 >= g_attn_tc_min && m->G <= 8) ? 1 : 0;
+  if (p.attn_tc && scratch < ATC_SMEM_BYTES) scratch = ATC_SMEM_BYTES;
   if (c.hidden > 8192) return fail(DN_EINVAL, "hidden > 8192 unsupported by the step kernel's RMSNorm staging");
   scratch = (scratch + 1023) / 1024 * 1024;
   const int tail = 2 * MK_MAX_STAGES * 8 + 64 * 4 + 128 * 4 + 2 * 8 * 16 * 4;   // barriers, misc scratch, RoPE table, row-block partials

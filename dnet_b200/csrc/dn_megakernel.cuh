@@ -98,6 +98,7 @@ struct MkParams {
   const int* bounds;         // optional [4 phases][grid+1] row boundaries (calibrated partition), else equal split
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
+  int attn_tc;               // 1: long-context attention phase on mma.sync with K/V tiles staged in shared memory (mk_attention_tc)
   // quantised KV (dn_kvquant.cuh): 0 = bf16 pages; 4 / 8 = packed pages, two-pass attention
   int kv_bits;
   bf16* kv_stage;            // bf16 staging pool the q/k/v epilogue writes the new K/V row into
@@ -664,7 +665,24 @@ __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const
 // split's tiles round-robin, merging through shared memory.  A second CTA split per head is only
 // added once every warp already has `attn_chunk` tokens, so short contexts need no cross-CTA
 // merge at all (S == 1: the CTA writes the normalised head output directly).
+constexpr int ATC_TOK = 16;                           // tokens per warp tile of the tensor-core attention
+constexpr int ATC_PITCH = HD * 2 + 16;                // 272-byte rows: the 8 row addresses of an ldmatrix hit 8 different bank groups
+constexpr int ATC_TILE_BYTES = ATC_TOK * ATC_PITCH;   // 4,352
+constexpr int ATC_WARP_BYTES = 2 * ATC_TILE_BYTES;    // K + V
+constexpr int ATC_SMEM_BYTES = MK_CW * ATC_WARP_BYTES;   // 69,632: lives in the activation scratch (dead during attention)
 __device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, int& S, int& tps) {
+  if (p.attn_tc) {
+    // tensor-core path: one CTA per (kv head, split) serves the whole GQA group; tiles of 16 tokens
+    const int n_tiles = (kv_len + ATC_TOK - 1) / ATC_TOK;
+    int smax = (int)gridDim.x / p.n_kv;
+    smax = max(1, min(smax, p.nsplit));
+    const int per_cta = MK_CW * 4;                    // a second split once every warp has 4 tiles (64 tokens)
+    int s = (n_tiles + per_cta - 1) / per_cta;
+    s = max(1, min(s, smax));
+    tps = (n_tiles + s - 1) / s;
+    S = (n_tiles + tps - 1) / tps;
+    return;
+  }
   const int n_tiles = (kv_len + 31) >> 5;
   int smax = (int)gridDim.x / p.n_heads;
   smax = max(1, min(smax, min(p.nsplit, 8)));
@@ -774,6 +792,173 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
     }
     cbar_sync();
   }
+}
+
+// ---------------------------------------------------------------------------------
+// attention phase on the tensor cores, for long contexts (bf16 pages).  The CUDA-core phase above is instruction
+// bound (~23 instructions per token and head, K/V read once per q head of a GQA group): at an 8K context it costs
+// ~29 us per layer against 5 us of KV bytes.  Here one CTA serves a (kv head, split) for the whole GQA group:
+//   * each of the 8 warps takes 16-token tiles round-robin and stages its K and V tile (2 x 4 KiB, contiguous
+//     inside a page) into its own shared-memory buffer with cp.async -- the buffers alias the activation scratch,
+//     which is dead between the q/k/v and o_proj phases;
+//   * S = Q K^T with mma.sync m16n8k16: A = Q of the group's G heads (rows >= G are zero), fragments held in
+//     registers for the whole phase; B = K rows through ldmatrix;
+//   * fp32 online softmax in the accumulator-fragment layout (a row's 16 scores sit in one quad);
+//   * O += P V with P re-used straight from the S accumulators as the A operand, split into bf16 hi + lo terms (the
+//     oracle keeps P in fp32), B = V through ldmatrix.trans;
+//   * warps are merged in fixed order; with S > 1 splits the (o, m, l) partials go through `part` exactly like the
+//     CUDA-core phase, so the o_proj staging merge is shared.
+// K/V bytes are read once per GROUP and ~50 tensor instructions replace ~1,500 ALU instructions per tile and group.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816_top(float& c0, float& c1, float& z0, float& z1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of A are zero (a1 = a3 = 0): their accumulators z0, z1 stay zero and are shared by every tile
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c0), "+f"(c1), "+f"(z0), "+f"(z1) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <int G>
+__device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane,
+                                                int S, int tps) {
+  const int kv_len = p.st->pos + 1;
+  const int n_tiles = (kv_len + ATC_TOK - 1) / ATC_TOK;
+  const float scale = 0.08838834764831845f;
+  const int task = blockIdx.x;
+  if (task >= p.n_kv * S) return;                              // CTA-uniform
+  const int kvh = task / S, sp = task % S;
+  const int tile0 = sp * tps, tile1 = min(n_tiles, (sp + 1) * tps);
+  const int g = lane >> 2, t = lane & 3;
+  unsigned char* kt = scratch + (size_t)cw * ATC_WARP_BYTES;
+  unsigned char* vt = kt + ATC_TILE_BYTES;
+  const uint32_t kt_s = smem_u32(kt), vt_s = smem_u32(vt);
+  // Q fragments of the group's heads (row g = head kvh*G + g), all 8 k-steps of the 128 dims
+  uint32_t qa0[8], qa2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    qa0[j] = 0u; qa2[j] = 0u;
+    if (g < G) {
+      const bf16* qrow = p.qbuf + (size_t)(kvh * G + g) * HD + 16 * j + 2 * t;
+      qa0[j] = __ldcg(reinterpret_cast<const uint32_t*>(qrow));
+      qa2[j] = __ldcg(reinterpret_cast<const uint32_t*>(qrow + 8));
+    }
+  }
+  float o[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; }
+  float m = -INFINITY, l = 0.f, z0 = 0.f, z1 = 0.f;
+#pragma unroll 1
+  for (int tile = tile0 + cw; tile < tile1; tile += MK_CW) {
+    const int tk0 = tile * ATC_TOK, nt = min(ATC_TOK, kv_len - tk0);
+    const int phys = p.block_table[tk0 / PAGE];
+    const unsigned char* kg = reinterpret_cast<const unsigned char*>(L.kv_pool + (((size_t)phys * 2) * p.n_kv + kvh) * (PAGE * HD) + (size_t)(tk0 % PAGE) * HD);
+    const unsigned char* vg = kg + (size_t)p.n_kv * (PAGE * HD) * 2;
+    __syncwarp();                                              // the previous tile's ldmatrix reads are done
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                              // 256 chunks of 16 bytes per tile, 8 per lane
+      const int chunk = c * 32 + lane, row = chunk >> 4, col = chunk & 15;
+      const uint32_t so = (uint32_t)(row * ATC_PITCH + col * 16);
+      if (row < nt) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kt_s + so), "l"(kg + (size_t)row * (HD * 2) + col * 16) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vt_s + so), "l"(vg + (size_t)row * (HD * 2) + col * 16) : "memory");
+      } else {                                                 // rows past the context: finite zeros (masked P = 0 must not meet junk)
+        *reinterpret_cast<uint4*>(kt + so) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(vt + so) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- S = Q K^T for 16 tokens: two n-tiles of 8 tokens
+    float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+    {
+      const uint32_t ka = kt_s + (uint32_t)(((lane & 7) + ((lane >> 4) & 1) * 8) * ATC_PITCH + ((lane >> 3) & 1) * 16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(ka + j * 32, b0, b1, b2, b3);
+        mma_bf16_16816_top(s0a, s0b, z0, z1, qa0[j], qa2[j], b0, b1);
+        mma_bf16_16816_top(s1a, s1b, z0, z1, qa0[j], qa2[j], b2, b3);
+      }
+    }
+    // row g holds tokens {2t, 2t+1} (n-tile 0) and {8+2t, 9+2t} (n-tile 1)
+    float sv[4] = {s0a * scale, s0b * scale, s1a * scale, s1b * scale};
+    const int tk[4] = {2 * t, 2 * t + 1, 8 + 2 * t, 9 + 2 * t};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (tk[i] >= nt) sv[i] = -INFINITY;
+    float mt = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 1));
+    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 2));
+    const float m_new = fmaxf(m, mt);
+    float pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pv[i] = (sv[i] == -INFINITY) ? 0.f : exp2f((sv[i] - m_new) * LOG2E);
+    const float corr = exp2f((m - m_new) * LOG2E);             // m == -inf -> 0
+    float ls = (pv[0] + pv[1]) + (pv[2] + pv[3]);
+    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+    l = l * corr + ls;
+    m = m_new;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
+    // P as the A operand: hi + lo bf16 terms of the fp32 probabilities
+    const uint32_t ph0 = pack_bf16x2(pv[0], pv[1]), ph2 = pack_bf16x2(pv[2], pv[3]);
+    const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&ph0), h2 = *reinterpret_cast<const __nv_bfloat162*>(&ph2);
+    const uint32_t pl0 = pack_bf16x2(pv[0] - __low2float(h0), pv[1] - __high2float(h0));
+    const uint32_t pl2 = pack_bf16x2(pv[2] - __low2float(h2), pv[3] - __high2float(h2));
+    {
+      const uint32_t va = vt_s + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * ATC_PITCH + ((lane >> 4) & 1) * 16);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                            // 16 dims per iteration = two n-tiles
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(va + i * 32, b0, b1, b2, b3);
+        mma_bf16_16816_top(o[2 * i][0], o[2 * i][1], z0, z1, ph0, ph2, b0, b1);
+        mma_bf16_16816_top(o[2 * i][0], o[2 * i][1], z0, z1, pl0, pl2, b0, b1);
+        mma_bf16_16816_top(o[2 * i + 1][0], o[2 * i + 1][1], z0, z1, ph0, ph2, b2, b3);
+        mma_bf16_16816_top(o[2 * i + 1][0], o[2 * i + 1][1], z0, z1, pl0, pl2, b2, b3);
+      }
+    }
+  }
+  // ---- merge the 8 warps (fixed order), per head of the group
+  cbar_sync();                                                 // every warp is done with its tile buffers
+  float* wpart = reinterpret_cast<float*>(scratch);            // [MK_CW][G][132] floats (<= 33.8 KB)
+  if (g < G) {
+    float* row = wpart + ((size_t)cw * G + g) * 132;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(row + 8 * i + 2 * t) = make_float2(o[i][0], o[i][1]);
+    if (t == 0) { row[128] = m; row[129] = l; }
+  }
+  cbar_sync();
+  for (int e = threadIdx.x; e < G * HD; e += MK_CTHREADS) {
+    const int hg = e / HD, d = e % HD;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < MK_CW; ++w) M = fmaxf(M, wpart[((size_t)w * G + hg) * 132 + 128]);
+    float Ls = 0.f, acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < MK_CW; ++w) {
+      const float mw = wpart[((size_t)w * G + hg) * 132 + 128];
+      if (mw != -INFINITY) {
+        const float ew = exp2f((mw - M) * LOG2E);
+        Ls = fmaf(wpart[((size_t)w * G + hg) * 132 + 129], ew, Ls);
+        acc = fmaf(wpart[((size_t)w * G + hg) * 132 + d], ew, acc);
+      }
+    }
+    const int head = kvh * G + hg;
+    if (S == 1) {
+      p.attn[head * HD + d] = __float2bfloat16_rn(acc * (1.0f / Ls));
+    } else {
+      float* pp = p.part + ((size_t)head * p.nsplit + sp) * PART_STRIDE;
+      pp[d] = acc;
+      if (d == 0) { pp[128] = M; pp[129] = Ls; }
+    }
+  }
+  cbar_sync();
 }
 
 // ---------------------------------------------------------------------------------
@@ -1182,7 +1367,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   int att_S, att_tps;
   mk_attn_geometry(p, pos + 1, att_S, att_tps);
   const int att_tile0 = ((int)blockIdx.x % att_S) * att_tps + cw;        // this warp's first tile (if the CTA has an attention task)
-  const bool att_has = p.kv_bits == 0 && (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
+  const bool att_has = p.kv_bits == 0 && !p.attn_tc && (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
   // quantised KV: value of this CTA's head counter before any arrival of this launch (arrivals happen after the first grid barrier)
   const unsigned int tk_base = (p.kv_bits != 0 && (int)blockIdx.x < p.n_heads * att_S) ? __ldcg(p.head_tk + (int)blockIdx.x / att_S) : 0u;
   const int att_phys0 = att_has ? p.block_table[(att_tile0 << 5) / PAGE] : 0;
@@ -1245,6 +1430,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
     if (p.kv_bits == 8) mk_attention_q<G, 8>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
     else if (p.kv_bits == 4) mk_attention_q<G, 4>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
+    else if (p.attn_tc) mk_attention_tc<G>(p, L, scratch, cw, lane, att_S, att_tps);
     else mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
     mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);

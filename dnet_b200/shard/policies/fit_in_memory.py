@@ -31,6 +31,8 @@ class FitInMemoryPolicy(ComputePolicy):
         self._mode = "fit"
         self._run_arrays = {}            # tuple(run) -> ctypes int32 array handed to dn_shard_step
         self.sched_entries_done = 0      # decode steps launched from schedule frames (progress signal for drivers)
+        self.sched_host_s = 0.0          # host seconds spent inside _process_sched, and the entries it covered
+        self.sched_host_entries = 0
         from collections import deque
         self._tp_hist = deque()          # tensor-parallel head: recent schedule entries (None = bubble) ...
         self._tp_hist_base = 0           # ... the ring-wide index of hist[0] ...
@@ -106,6 +108,8 @@ class FitInMemoryPolicy(ComputePolicy):
         rt = self.runtime
         hop = rt.hop
         ticket = msg.sched_done
+        import time as _time
+        _t0 = _time.perf_counter()
         try:
             with rt._model_lock:
                 if not cc.model_ready(rt) or hop is None or not hop.connected:
@@ -157,6 +161,8 @@ class FitInMemoryPolicy(ComputePolicy):
         except Exception as e:
             logger.exception("Error launching scheduled decode steps: %s", e)
         finally:
+            self.sched_host_s += _time.perf_counter() - _t0      # host time spent launching (drivers report it per entry)
+            self.sched_host_entries += len(msg.sched or ())
             if ticket is not None:
                 ev = None
                 try:

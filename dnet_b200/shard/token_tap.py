@@ -89,17 +89,16 @@ class TokenTap:
         return n
 
     def _run(self) -> None:
-        idle = 0
+        # Never spin: this thread shares the GIL with the compute thread that launches the step kernels, and a
+        # Python busy loop here delays those launches (measured at 8 shards: ~50 us per slot on the finalising shard).
+        # A 50 us nap between polls costs a token 25 us of observation latency on average and nothing else.
         while self._running:
-            if self.poll_once():
-                idle = 0
-                continue
-            idle += 1
+            self.poll_once()
             if self.in_flight() == 0:
                 self._wake.wait(timeout=0.05)
                 self._wake.clear()
-            elif idle > 50:
-                time.sleep(2e-5)
+            else:
+                time.sleep(5e-5)
 
     def start(self) -> None:
         if self._thread is None:
