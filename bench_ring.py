@@ -74,10 +74,11 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         cfg["num_hidden_layers"] = args.layers
     L, H = cfg["num_hidden_layers"], cfg["hidden_size"]
     K, W = args.steps, args.warmup
+    ts_lag = max(0, int(os.environ.get("DNET_TRANSPORT_HEAD_TP_LAG", "1")))
     tp_wanted = world >= 2 and (args.head_tp == "on" or (args.head_tp == "auto" and world >= 4))
     # sequences in flight: one per shard keeps a plain ring busy; with the lm_head tensor-parallel over the ring a
     # token is finalised one slot after its last layer, so S + 1 sequences keep all S shards busy
-    NS = (world + (1 if tp_wanted else 0)) if args.in_flight <= 0 else args.in_flight
+    NS = (world + (1 + ts_lag if tp_wanted else 0)) if args.in_flight <= 0 else args.in_flight
     if args.split == "equal" or world == 1 or (tp_wanted and L % world == 0):
         split = even_split(L, world)            # tensor-parallel head: every shard streams the same bytes with equal counts
     else:
@@ -131,6 +132,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     prompts = [torch.randint(0, cfg["vocab_size"], (PROMPT_LEN,), generator=g).tolist() for _ in range(NS)]
     nonces = [f"n{n}" for n in range(NS)]
     got = {n: [] for n in nonces}            # tokens as the API receives them
+    stamps = []                              # host arrival time of every token (steady-state rate, start-up share)
     stream = rt.compute_stream
     pol = rt.policy
 
@@ -147,6 +149,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
 
         def sink(msg):
             got.setdefault(msg.nonce, []).append((int(msg.token_id), float(msg.logprob)))
+            stamps.append(time.perf_counter())
         ad.token_sink = sink                    # decode tokens: in-process, straight from the TokenTap
         if tp:                                  # the tail's first tokens (prefill) arrive over gRPC SendToken
             api.manager.resolve_request = lambda nonce, res: got.setdefault(nonce, []).append((int(res.token_id), float(res.logprob)))
@@ -201,6 +204,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         time.sleep(0.3)
     l0 = lib.dn_launch_count()
     h0, n0 = pol.sched_host_s, pol.sched_host_entries
+    stamp0 = len(stamps)
     tw0 = time.perf_counter()
     ms_local, wall = run_steps(K, 1 + W, W * NS, True)
     host_us = (pol.sched_host_s - h0) / max(1, pol.sched_host_entries - n0) * 1e6
@@ -224,6 +228,16 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
 
     ms = allmax(ms_local)
     host_us_max = allmax(host_us)
+    steady = None
+    if on_api:
+        ts_ = stamps[stamp0:stamp0 + K * NS]
+        if len(ts_) >= 20:
+            a, b = len(ts_) // 10, len(ts_) - len(ts_) // 10 - 1
+            steady = {"tok_s_middle_80pct": (b - a) / (ts_[b] - ts_[a]), "first_token_ms_after_lease": (ts_[0] - tw0) * 1e3,
+                      "note": "host arrival times of the timed tokens: rate between the 10 % and 90 % marks, and how long after "
+                              "submitting the leases the first token arrived (lease -> schedule frames round the ring -> pipeline fill)"}
+    steady_v = allmax(steady["tok_s_middle_80pct"] if steady else 0.0)
+    first_ms = allmax(steady["first_token_ms_after_lease"] if steady else 0.0)
     e2e_s = allmax(wall if wall is not None else 0.0)
     launches_all = allsum(launches)
     step_err = int(allmax(float(step_err)))
@@ -315,6 +329,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
                                  "host_us_per_entry_max_rank": host_us_max}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
             "ring_hop_us": hop,
+            "steady_state": {"tok_s_middle_80pct": steady_v, "first_token_ms_after_lease": first_ms},
             "check": {"nonce0_token_after_steps": W + K, "token": check_token, "all_tokens_valid": tokens_ok,
                       "oracle_full_depth": parity,
                       "note": "nonce 0's token after W+K decode steps: identical at every N and for both splits"},

@@ -53,6 +53,9 @@ class TransportSettings:  # reference config.py:108-127 (prefix DNET_TRANSPORT_)
     sched_frames_in_flight: int = field(default_factory=lambda: _env("DNET_TRANSPORT_SCHED_DEPTH", 3, int))
     # lm_head tensor-parallel over the ring during on-device decode: "auto" (rings of >= 4 shards), "on", "off"
     head_tp: str = field(default_factory=lambda: _env("DNET_TRANSPORT_HEAD_TP", "auto"))
+    # extra schedule entries between a token's last layer and its head parts: 0 couples every shard to the last
+    # shard's previous kernel (they all wait for its broadcast), 1 gives that broadcast a whole slot of slack
+    head_tp_lag: int = field(default_factory=lambda: _env("DNET_TRANSPORT_HEAD_TP_LAG", 1, int))
     compress: bool = False
     compress_min_bytes: int = 65536
 

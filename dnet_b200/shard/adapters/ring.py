@@ -111,6 +111,7 @@ class RingAdapter(TopologyAdapter):
         self.ring_size = 1
         self.ring_pos = 0
         self.head_tp = False                  # lm_head split over the ring's shards during on-device decode
+        self.head_tp_lag = max(0, int(getattr(self.transport_settings, "head_tp_lag", 1)))
         self._tp_flush = 0                    # head: bubble entries still owed so the last tokens' head parts run
         self._sched_index = 0                 # head: ring-wide index of the next schedule entry
         self._lane_last_idx: Dict[int, int] = {}
@@ -269,7 +270,7 @@ class RingAdapter(TopologyAdapter):
             if self.head_tp:
                 row0, row1 = await asyncio.get_running_loop().run_in_executor(rt.executor, rt.load_head_slice,
                                                                                self.ring_pos, self.ring_size)
-                rt.tp_head = {"S": self.ring_size, "r": self.ring_pos, "rows": (row0, row1)}
+                rt.tp_head = {"S": self.ring_size, "r": self.ring_pos, "rows": (row0, row1), "lag": self.head_tp_lag}
                 logger.info("Shard %s: lm_head tensor-parallel over %d shards, this shard rows %d..%d", rt.shard_id,
                             self.ring_size, row0, row1 - 1)
             # tokens surface where they are finalised: the tail shard, or the head shard with a tensor-parallel head
@@ -441,7 +442,7 @@ class RingAdapter(TopologyAdapter):
         earliest: bubble entries are inserted wherever that distance would be violated, and S + 1 bubbles flush the
         head parts of the last tokens once nothing is leased any more."""
         entries: List[Tuple[int, int]] = []
-        gap = self.ring_size + 1 if self.head_tp else 0
+        gap = self.ring_size + 1 + self.head_tp_lag if self.head_tp else 0
         for _ in range(self.rounds_per_frame):
             live = [(self._streams.lane_ctx(n), n) for n, left in self._leases.items() if left > 0]
             live = sorted(((c.lane, n, c) for c, n in live if c is not None and c.lane >= 0), key=lambda x: x[0])

@@ -191,7 +191,7 @@ class FitInMemoryPolicy(ComputePolicy):
         rt = self.runtime
         hop, mesh = rt.hop, rt.hop.mesh
         lib = _cabi.load()
-        S, r = int(rt.tp_head["S"]), int(rt.tp_head["r"])
+        S, r, lag = int(rt.tp_head["S"]), int(rt.tp_head["r"]), int(rt.tp_head.get("lag", 0))
         hist = self._tp_hist
         s = rt.compute_stream_ptr
         now = time.perf_counter()
@@ -203,7 +203,7 @@ class FitInMemoryPolicy(ComputePolicy):
             if len(hist) > 64:
                 hist.popleft()
                 self._tp_hist_base += 1
-            j = idx - (S - r) - self._tp_hist_base
+            j = idx - (S - r) - lag - self._tp_hist_base
             due = hist[j] if 0 <= j < len(hist) else None
             tp = _cabi.TpArgs()
             if due is not None:

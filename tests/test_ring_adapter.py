@@ -581,7 +581,7 @@ def test_tp_head_schedule_keeps_a_requests_steps_S_plus_1_entries_apart_and_flus
     for n_req, steps in ((1, 3), (2, 4), (5, 3), (7, 2)):
         ad, rt = make_adapter(assigned_next={0})
         rt._assigned_set = {0}
-        ad.total_layers, ad.ring_size, ad.head_tp, ad.rounds_per_frame = 8, S, True, 3
+        ad.total_layers, ad.ring_size, ad.head_tp, ad.rounds_per_frame, ad.head_tp_lag = 8, S, True, 3, 0
         ad._streams.configure_lanes(8)
         for i in range(n_req):
             ad._streams.claim_lane(f"r{i}").params["seq0"] = 1
