@@ -439,6 +439,7 @@ def main():
                     help="decode: BASELINE configs[1] (the bench contract); swap: configs[3], Llama-3-70B layer swap (bench_swap.py)")
     ap.add_argument("--swap-window", type=int, default=4, help="--config swap: window_size = residency_size (HBM layer slots per window)")
     ap.add_argument("--swap-resident-windows", type=int, default=1)
+    ap.add_argument("--attn-tc", type=int, default=-1, help="step kernel: tensor-core attention phase at long contexts (-1 = library default: on)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -121,6 +121,8 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
             lib.dn_set_option(k.encode(), v)
     if args.attn_chunk:
         lib.dn_set_option(b"attn_chunk", args.attn_chunk)
+    if args.attn_tc >= 0:
+        lib.dn_set_option(b"attn_tc", args.attn_tc)
     barrier()
     log(f"rank {rank}: layers {mine[0]}..{mine[-1]} loaded + topology configured in {time.perf_counter() - t_load:.1f}s "
         f"(hop lanes {ad.n_lanes}, head={ad.is_head} tail={ad.is_tail})")

@@ -113,6 +113,10 @@ class RingAdapter(TopologyAdapter):
         self.head_tp = False                  # lm_head split over the ring's shards during on-device decode
         self.head_tp_lag = max(0, int(getattr(self.transport_settings, "head_tp_lag", 1)))
         self._tp_flush = 0                    # head: bubble entries still owed so the last tokens' head parts run
+        self.advertise_addr: Optional[str] = None   # this shard's gRPC address (host:port), set by whoever starts its server
+        self._ring_addrs: List[Optional[str]] = []  # gRPC address of every ring position (from the census), None = unknown
+        self._fan_channels: Dict[int, Any] = {}
+        self._fan_stubs: Dict[int, Any] = {}
         self._sched_index = 0                 # head: ring-wide index of the next schedule entry
         self._lane_last_idx: Dict[int, int] = {}
 
@@ -199,6 +203,13 @@ class RingAdapter(TopologyAdapter):
         self.api_stub = None
         self.api_address = None
         self._leases.clear()
+        for ch in self._fan_channels.values():
+            try:
+                await ch.close()
+            except Exception:
+                pass
+        self._fan_channels.clear()
+        self._fan_stubs.clear()
         self._teardown_hop()
 
     async def admit_frame(self, request) -> None:
@@ -245,7 +256,7 @@ class RingAdapter(TopologyAdapter):
                 # ring census: ask for the endpoint k hops ahead until our own comes back
                 ring: list = []
                 for k in range(64):
-                    ep = await exchange(hop.endpoint(), k)
+                    ep = await exchange(self._endpoint(hop), k)
                     if ep is None:
                         break
                     if self._ep_id(ep) == str(rt.shard_id):
@@ -302,6 +313,11 @@ class RingAdapter(TopologyAdapter):
             rt.hop = None
             rt.on_emit = None
 
+    def _endpoint(self, hop) -> dict:
+        ep = hop.endpoint()
+        ep["grpc_addr"] = self.advertise_addr
+        return ep
+
     @staticmethod
     def _ep_id(ep) -> str:
         return str(ep.shard_id if hasattr(ep, "shard_id") else ep.get("shard_id"))
@@ -323,6 +339,8 @@ class RingAdapter(TopologyAdapter):
             return
         h = heads[0]
         order = order[h:] + order[:h]                          # ring positions 0..S-1
+        self._ring_addrs = [(self.advertise_addr if ep is hop else (None if isinstance(ep, HopLink) else ep.get("grpc_addr")))
+                            for ep in order]
         self.ring_size = S
         self.ring_pos = next(i for i, ep in enumerate(order) if ep is hop)
         want = self.head_tp_mode in ("on", "1", "true") or (self.head_tp_mode == "auto" and S >= 4)
@@ -497,14 +515,32 @@ class RingAdapter(TopologyAdapter):
                 # FIFO with prompts: through the same compute queue, and on to the successor
                 await self._enqueue_compute(msg)
                 if not self.is_tail:
-                    await self._connect_next_node()
-                    await self._forward_activation(self._sched_request(entries))
+                    await self._publish_schedule(entries)
                 self.stats["frames_sched"] += 1
             except asyncio.CancelledError:
                 break
             except Exception as e:
                 logger.error("schedule worker error: %s", e)
                 await asyncio.sleep(0.01)
+
+    async def _publish_schedule(self, entries) -> None:
+        """Head shard: get a schedule frame to every other shard.  When the census told us every shard's gRPC address
+        the frame is sent to all of them directly (batch_size = 2 marks it "do not relay"), so a shard S hops away
+        starts launching one RPC after the head instead of S relays later; otherwise it is relayed round the ring."""
+        req = self._sched_request(entries)
+        targets = [i for i in range(self.ring_size) if i != self.ring_pos]
+        if len(self._ring_addrs) == self.ring_size and all(self._ring_addrs[i] for i in targets) and aio_grpc is not None:
+            req.activation.batch_size = 2
+            for i in targets:
+                stub = self._fan_stubs.get(i)
+                if stub is None:
+                    ch = aio_grpc.insecure_channel(self._ring_addrs[i])
+                    self._fan_channels[i] = ch
+                    stub = self._fan_stubs[i] = _make_ring_stub(ch)
+                await self._stream_put(f"{req.nonce}@{i}", req, stub)
+            return
+        await self._connect_next_node()
+        await self._forward_activation(req)
 
     def _sched_message(self, entries) -> ActivationMessage:
         msg = ActivationMessage(nonce="", pool_id=-1, batch_size=1, shape=(len(entries),), dtype=fr.SCHED_DTYPE, layer_id=-1,
@@ -537,7 +573,7 @@ class RingAdapter(TopologyAdapter):
                 if dtype == fr.SCHED_DTYPE:
                     entries = fr.unpack_sched(activation.data)
                     await self._enqueue_compute(self._sched_message(entries))
-                    if not self.is_tail:
+                    if not self.is_tail and activation.batch_size != 2:      # 2 = sent to every shard directly by the head
                         await self._forward_activation(req)
                     continue
                 if dtype == fr.LEASE_DTYPE:
@@ -654,9 +690,9 @@ class RingAdapter(TopologyAdapter):
             await self._streams.cleanup_idle_streams()
             await asyncio.sleep(1.0)
 
-    async def _stream_put(self, nonce: str, request) -> bool:
-        """One frame onto the nonce's stream to the next node (created on first use)."""
-        stub = self.next_node_stub
+    async def _stream_put(self, nonce: str, request, stub=None) -> bool:
+        """One frame onto the stream keyed ``nonce`` (created on first use) to the next node, or to ``stub``."""
+        stub = stub or self.next_node_stub
         if not (self._streaming_enabled and stub):
             return False
         ctx = await self._streams.get_or_create_stream(nonce, lambda it: stub.StreamActivations(it))

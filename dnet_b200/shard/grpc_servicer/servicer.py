@@ -37,7 +37,9 @@ class GrpcServicer(DnetRingServiceServicer):
                 if hop is None:
                     return pb2.ActivationResponse(success=False, message="no hop lanes on this shard (yet)",
                                                   node_id=str(self.shard.node_id))
-                return pb2.ActivationResponse(success=True, message=json.dumps(hop.endpoint()), node_id=str(self.shard.node_id))
+                ep = hop.endpoint()
+                ep["grpc_addr"] = getattr(self.shard.adapter, "advertise_addr", None)
+                return pb2.ActivationResponse(success=True, message=json.dumps(ep), node_id=str(self.shard.node_id))
             await self.shard.admit_frame(request)
             return pb2.ActivationResponse(success=True, message="Activation processed successfully",
                                           node_id=str(self.shard.node_id))

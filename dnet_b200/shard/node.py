@@ -46,6 +46,7 @@ class ShardNode:
         self.runtime = runtime or ShardRuntime(shard_id=shard_id, queue_size=queue_size)
         self._lt = _LoopThread(f"dnet-shard-{shard_id}")
         self.adapter = self._lt.call(self._make(lambda: RingAdapter(self.runtime, None, transport_settings)))
+        self.adapter.advertise_addr = f"{host}:{grpc_port}"
         self.shard = Shard(shard_id, self.adapter)
         self.server = GrpcServer(grpc_port, self.shard, host=host)
         self._started = False
