@@ -669,14 +669,15 @@ constexpr int ATC_TOK = 16;                           // tokens per warp tile of
 constexpr int ATC_PITCH = HD * 2 + 16;                // 272-byte rows: the 8 row addresses of an ldmatrix hit 8 different bank groups
 constexpr int ATC_TILE_BYTES = ATC_TOK * ATC_PITCH;   // 4,352
 constexpr int ATC_WARP_BYTES = 2 * ATC_TILE_BYTES;    // K + V
-constexpr int ATC_SMEM_BYTES = MK_CW * ATC_WARP_BYTES;   // 69,632: lives in the activation scratch (dead during attention)
+constexpr int ATC_WARPS = 6;                          // warps that own tiles; all 8 keep draining the weight ring into tensor memory
+constexpr int ATC_SMEM_BYTES = ATC_WARPS * ATC_WARP_BYTES;   // 52,224: lives in the activation scratch (dead during attention)
 __device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, int& S, int& tps) {
   if (p.attn_tc) {
     // tensor-core path: one CTA per (kv head, split) serves the whole GQA group; tiles of 16 tokens
     const int n_tiles = (kv_len + ATC_TOK - 1) / ATC_TOK;
     int smax = (int)gridDim.x / p.n_kv;
     smax = max(1, min(smax, p.nsplit));
-    const int per_cta = MK_CW * 4;                    // a second split once every warp has 4 tiles (64 tokens)
+    const int per_cta = ATC_WARPS * 4;                // a second split once every tile warp has 4 tiles (64 tokens)
     int s = (n_tiles + per_cta - 1) / per_cta;
     s = max(1, min(s, smax));
     tps = (n_tiles + s - 1) / s;
@@ -825,7 +826,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 template <int G>
 __device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer& L, unsigned char* scratch, int cw, int lane,
-                                                int S, int tps) {
+                                                int S, int tps, MkRing& ring, MkCons& cs, unsigned int* done_ctr) {
   const int kv_len = p.st->pos + 1;
   const int n_tiles = (kv_len + ATC_TOK - 1) / ATC_TOK;
   const float scale = 0.08838834764831845f;
@@ -852,8 +853,11 @@ __device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer
 #pragma unroll
   for (int i = 0; i < 16; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; }
   float m = -INFINITY, l = 0.f, z0 = 0.f, z1 = 0.f;
+  // While a tile is in flight every warp drains ready weight stages into its tensor-memory slice (the same parking the
+  // grid barriers use): the phase is latency bound (one L2 / HBM round trip per tile), so HBM keeps streaming the
+  // o_proj / gate / up weights underneath it instead of idling with a full ring.
 #pragma unroll 1
-  for (int tile = tile0 + cw; tile < tile1; tile += MK_CW) {
+  for (int tile = tile0 + cw; cw < ATC_WARPS && tile < tile1; tile += ATC_WARPS) {
     const int tk0 = tile * ATC_TOK, nt = min(ATC_TOK, kv_len - tk0);
     const int phys = p.block_table[tk0 / PAGE];
     const unsigned char* kg = reinterpret_cast<const unsigned char*>(L.kv_pool + (((size_t)phys * 2) * p.n_kv + kvh) * (PAGE * HD) + (size_t)(tk0 % PAGE) * HD);
@@ -872,6 +876,7 @@ __device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (cs.park) { if (mk_try_park(ring, cs, lane)) mk_try_park(ring, cs, lane); }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     // ---- S = Q K^T for 16 tokens: two n-tiles of 8 tokens
@@ -924,10 +929,26 @@ __device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer
       }
     }
   }
-  // ---- merge the 8 warps (fixed order), per head of the group
+  // ---- every warp keeps parking until the tile warps are done (a blocking barrier would stop the ring draining:
+  //      a ring slot is only released once all 8 warps took their slice of it)
+  if (cw < ATC_WARPS) { __syncwarp(); if (lane == 0) atomicAdd(done_ctr, 1u); }
+  if (cs.park) {
+    const unsigned long long t0 = gtimer();
+    unsigned it = 0;
+    for (;;) {
+      unsigned int dn = 0;
+      if (lane == 0) dn = ld_acquire_cta(done_ctr);
+      dn = __shfl_sync(0xffffffffu, dn, 0);
+      if (dn >= (unsigned)ATC_WARPS) break;
+      const bool parked = mk_try_park(ring, cs, lane);
+      if (!parked && (++it & 1023u) == 0 && gtimer() - t0 > MK_TIMEOUT_NS) { atomicExch(p.err, 3u); break; }
+    }
+  }
+  // ---- merge the tile warps (fixed order), per head of the group
   cbar_sync();                                                 // every warp is done with its tile buffers
-  float* wpart = reinterpret_cast<float*>(scratch);            // [MK_CW][G][132] floats (<= 33.8 KB)
-  if (g < G) {
+  if (threadIdx.x == 0) *done_ctr = 0u;                        // re-armed for the next layer (ordered by the barriers below)
+  float* wpart = reinterpret_cast<float*>(scratch);            // [ATC_WARPS][G][132] floats (<= 25.3 KB)
+  if (cw < ATC_WARPS && g < G) {
     float* row = wpart + ((size_t)cw * G + g) * 132;
 #pragma unroll
     for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(row + 8 * i + 2 * t) = make_float2(o[i][0], o[i][1]);
@@ -938,10 +959,10 @@ __device__ __forceinline__ void mk_attention_tc(const MkParams& p, const MkLayer
     const int hg = e / HD, d = e % HD;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < MK_CW; ++w) M = fmaxf(M, wpart[((size_t)w * G + hg) * 132 + 128]);
+    for (int w = 0; w < ATC_WARPS; ++w) M = fmaxf(M, wpart[((size_t)w * G + hg) * 132 + 128]);
     float Ls = 0.f, acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < MK_CW; ++w) {
+    for (int w = 0; w < ATC_WARPS; ++w) {
       const float mw = wpart[((size_t)w * G + hg) * 132 + 128];
       if (mw != -INFINITY) {
         const float ew = exp2f((mw - M) * LOG2E);
@@ -1230,7 +1251,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   unsigned int* tmem_slot = reinterpret_cast<unsigned int*>(red + 56);
   unsigned int* bar_req = reinterpret_cast<unsigned int*>(red + 57);
   unsigned int* bar_done = reinterpret_cast<unsigned int*>(red + 58);
-  if (threadIdx.x == 0) { *consumed = 0u; *bar_req = 0u; *bar_done = 0u; *tmem_slot = 0u; red[60] = 0.f; }
+  if (threadIdx.x == 0) { *consumed = 0u; *bar_req = 0u; *bar_done = 0u; *tmem_slot = 0u; red[60] = 0.f; red[61] = 0.f; }
   if (p.park && warp == 0) {
     // all 512 TMEM columns: 8 consumer warps x 8 parked stages x 32 columns (one CTA per SM, so nothing else wants them)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -1430,7 +1451,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
     if (p.kv_bits == 8) mk_attention_q<G, 8>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
     else if (p.kv_bits == 4) mk_attention_q<G, 4>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
-    else if (p.attn_tc) mk_attention_tc<G>(p, L, scratch, cw, lane, att_S, att_tps);
+    else if (p.attn_tc) mk_attention_tc<G>(p, L, scratch, cw, lane, att_S, att_tps, ring, cs, reinterpret_cast<unsigned int*>(red + 61));
     else mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
     mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
