@@ -62,3 +62,41 @@ def test_same_token_at_every_shard_count():
         d = _load(name)
         toks.add((d["check"]["nonce0_token_after_steps"], d["check"]["token"]))
     assert len(toks) == 1, toks
+
+
+# ---- round 2: every N runs through the product transport (ShardNode / RingAdapter / ApiNode)
+@pytest.mark.parametrize("name,n", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)])
+def test_r02_our_arm_line(name, n):
+    d = _load(name)
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "decode tok/s Llama-3-8B bs=1" and d["unit"] == "tok/s" and d["n_gpus"] == n
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "bf16" and d["data"] == "synthetic" and d["warmup"] >= 3
+    ns = d["config"]["sequences_in_flight"]
+    assert abs(d["value"] - ns * 1e3 / d["ms_per_step"]) / d["value"] < 1e-6
+    assert d["gpu_launches"] >= d["steps"] * ns                      # one fused step kernel per (sequence, step) per shard
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] >= 0.9 * d["value"], "the API-side rate must follow the device-timed one (round 1: it fell with N)"
+    assert d["config"]["step_error"] == 0 and d["check"]["all_tokens_valid"] is True
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and 0.5 < r["frac"] < 1.1
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+    b = d["cpu_baseline"]
+    if b is not None:
+        assert b["kind"] == "port" and b["cores"] >= 1 and "extrapolated" not in b["sample"].replace("nothing extrapolated", "")
+    if n == 1:
+        assert r["traffic"] and 0.99 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.05
+        od = d["check"]["oracle_full_depth"]
+        assert od and od["compared"] >= 8 and od["equal_prefix"] >= 1
+    else:
+        assert d["ring_hop_us"]["activation_8k"] > 0
+
+
+def test_r02_same_token_at_every_shard_count():
+    toks = set()
+    for name in ("r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"):
+        d = _load(name)
+        toks.add((d["check"]["nonce0_token_after_steps"], d["check"]["token"]))
+    assert len(toks) == 1, toks
