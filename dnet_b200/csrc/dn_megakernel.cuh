@@ -1412,6 +1412,24 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
       tma_prefetch_l2(kb + (size_t)p.n_kv * (PAGE * HD), (uint32_t)nt0 * HD * 2u, polk);
     }
 
+    if (p.attn_tc && cw < ATC_WARPS && (int)blockIdx.x < p.n_kv * att_S) {
+      // tensor-core attention: pull every K/V tile this warp will touch toward L2 NOW, so that the HBM reads of the
+      // context overlap the q/k/v phase and the attention phase's cp.async copies hit L2 (a warp's tiles are otherwise
+      // fetched one after the other, each a full loaded-HBM round trip).  The context of this layer is static except
+      // for the row the q/k/v epilogue is about to write, which L2 keeps coherent.
+      const int kvh_p = (int)blockIdx.x / att_S, sp_p = (int)blockIdx.x % att_S;
+      const int ntl = (pos + ATC_TOK) / ATC_TOK;                       // tiles of pos + 1 tokens
+      const int t1 = min(ntl, (sp_p + 1) * att_tps);
+      const uint64_t polk = l2_policy_evict_last();
+      for (int tile = sp_p * att_tps + cw + lane * ATC_WARPS; tile < t1; tile += 32 * ATC_WARPS) {
+        const int tk0 = tile * ATC_TOK, ntk = min(ATC_TOK, pos + 1 - tk0);
+        const int phys = p.block_table[tk0 / PAGE];
+        const bf16* kb = L.kv_pool + (((size_t)phys * 2) * p.n_kv + kvh_p) * (PAGE * HD) + (size_t)(tk0 % PAGE) * HD;
+        tma_prefetch_l2(kb, (uint32_t)ntk * HD * 2u, polk);
+        tma_prefetch_l2(kb + (size_t)p.n_kv * (PAGE * HD), (uint32_t)ntk * HD * 2u, polk);
+      }
+    }
+
     // ---- P1: RMSNorm -> q/k/v -> RoPE -> paged-KV append
     mk_stage_rmsnorm(xs, red, cur, L.w[MK_W_LN1], p.H, p.eps);
     MK_STAMP(1);
