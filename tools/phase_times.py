@@ -12,13 +12,16 @@ from tests.helpers import token_message
 
 torch.cuda.set_device(0); _cabi.init(0); lib = _cabi.load()
 cfg = dict(B.LLAMA3_8B); L = cfg["num_hidden_layers"]
-rt = ShardRuntime(0); rt.kv_cache_config.max_tokens = 512
+PROMPT = int(os.environ.get("PROMPT", "128"))
+rt = ShardRuntime(0); rt.kv_cache_config.max_tokens = PROMPT + 64
 rt.load_model_core(ShardLoadModelRequest(model_path=SyntheticSource(cfg, 0), total_layers=L, layers=list(range(L)), window_size=L, residency_size=L, kv_bits="fp16"))
 lib.dn_set_option(b"pf_depth", int(os.environ.get("PF", "0")))
 lib.dn_set_option(b"inflight", int(os.environ.get("INFLIGHT", "0")))
+if "ATTN_TC" in os.environ:
+    lib.dn_set_option(b"attn_tc", int(os.environ["ATTN_TC"]))
 pol = rt.policy
 g = torch.Generator().manual_seed(1234)
-prompt = torch.randint(0, cfg["vocab_size"], (128,), generator=g).tolist()
+prompt = torch.randint(0, cfg["vocab_size"], (PROMPT,), generator=g).tolist()
 pol.process(token_message(rt, "d", prompt)); first = rt.activation_send_queue.get_nowait()
 ns = rt.get_or_make_kv("d"); ns.kv.set_token(first.token_id, rt.compute_stream_ptr)
 run = list(range(L))
