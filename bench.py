@@ -367,7 +367,7 @@ def single_gpu_extras(args, rt, cfg: dict, K: int, ms: float) -> dict:
         try:
             tj = json.loads(tp.read_text())
             traffic = tj.get("k_shard_step_dram_bytes_per_launch")
-            src = tj.get("source", "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full)")
+            src = tj.get("k_shard_step_source", "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full)")
         except Exception:
             pass
     G = cfg["num_attention_heads"] // cfg["num_key_value_heads"]

@@ -46,7 +46,7 @@ static int g_park = 1;          // step kernel: park ready ring stages in tensor
 static int g_inflight = 2;      // step kernel: ring stages with loads outstanding while the consumers are not starving (barriers, staging); measured caps 2/3/4/5/none = 357/381/374/369/366 tok/s static, 2-when-idle/3-when-starving +0.7 % on top
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
 static int g_attn_tc = 1;       // step kernel: tensor-core attention phase (shared-memory K/V tiles + mma) for long contexts ...
-static int g_attn_tc_min = 4096;   // ... from this many tokens of context on (bf16 KV)
+static int g_attn_tc_min = 12288;   // ... from this many tokens of context on (bf16 KV)
 static int g_mk_debug = 0;
 static int g_pf_depth = 0;    // step kernel: L2 prefetch look-ahead in 32 KB ring stages (measured: <= +2% at 8,
                               // harmful beyond -- 148 SMs x depth x 32 KB must stay well inside one L2 partition)

@@ -74,4 +74,4 @@ def test_tensor_core_decode_attention_against_oracle_and_cuda_core_path(cuda_lib
               f"cuda-core {max(rel_inf(got[0][i], ref[i]) for i in range(steps)):.2e}; between paths {between:.2e} (tol {tol:.2e})")
     finally:
         cuda_lib.dn_set_option(b"attn_tc", 1)
-        cuda_lib.dn_set_option(b"attn_tc_min", 4096)
+        cuda_lib.dn_set_option(b"attn_tc_min", 12288)
