@@ -675,20 +675,21 @@ class RingAdapter(TopologyAdapter):
                 continue
             await (self.token_tx_q if msg.is_final else self.ring_tx_q).put(msg)
 
+    async def _pump(self, q: asyncio.Queue, deliver) -> None:
+        """drain one egress queue; keeps going after stop until the queue is empty"""
+        while self.running or not q.empty():
+            await deliver(await q.get())
+
     async def _ring_tx_worker(self):
-        while self.running or not self.ring_tx_q.empty():
-            msg = await self.ring_tx_q.get()
-            await self._send_activation(msg)
+        await self._pump(self.ring_tx_q, self._send_activation)
 
     async def _token_tx_worker(self):
-        while self.running or not self.token_tx_q.empty():
-            msg = await self.token_tx_q.get()
-            await self._send_token(msg)
+        await self._pump(self.token_tx_q, self._send_token)
 
     async def _stream_sweeper(self):
         while self.running:
-            await self._streams.cleanup_idle_streams()
             await asyncio.sleep(1.0)
+            await self._streams.cleanup_idle_streams()
 
     async def _stream_put(self, nonce: str, request, stub=None) -> bool:
         """One frame onto the stream keyed ``nonce`` (created on first use) to the next node, or to ``stub``."""

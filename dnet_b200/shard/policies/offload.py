@@ -79,6 +79,45 @@ class OffloadPolicy(ComputePolicy):
             fut = rt.executor.submit(self._prepare_window_blocking, next_window)
         self._prepared_by_nonce[nonce] = (next_window, fut)
 
+    def _drop_window(self, layers) -> None:
+        self.weight_cache.evict_layers(layers)
+        self.runtime.model.unload_layers(layers)
+        for lid in layers:
+            self._bound_versions.pop(lid, None)
+
+    def _retire_window(self, window_layers, did_early_swap: bool) -> None:
+        """What stays resident after a window ran (behaviour of reference offload.py:253-312).
+        offload, 1 resident window : the window that just ran is evicted at once (its slots take the next one)
+        offload, n resident windows: windows are kept in arrival order; with eager unloading the oldest go as soon
+                                     as more than n are remembered (deferred unloading leaves that to the cache's LRU)
+        sliding_fit, 1 window      : delta swap -- of the previous window only what still fits beside the new one stays
+                                     (already done up front when the policy swapped early)
+        sliding_fit, n windows     : just remembered; the weight cache's budget does the rest"""
+        curr = list(window_layers)
+        single = int(self._resident_windows) <= 1
+        if self._mode != "sliding_fit":
+            self._recent_windows.append(curr)
+            if single:
+                self._drop_window(self._recent_windows.pop(0))
+            elif not self._defer_unload:
+                keep = max(1, int(self._resident_windows))
+                while len(self._recent_windows) > keep:
+                    self._drop_window(self._recent_windows.pop(0))
+            return
+        if not single:
+            self._recent_windows.append(curr)
+            return
+        if did_early_swap:
+            return
+        if not self._recent_windows:
+            self._recent_windows.append(curr)
+            return
+        prev = self._recent_windows.pop(0)
+        self._delta_swap_eviction(curr, prev)
+        room = max(0, max(1, int(self.window_size or 1)) - len(curr))
+        survivors = [lid for lid in prev if lid not in curr]
+        self._recent_windows.append((survivors[-room:] if room else []) + curr)
+
     def process(self, msg: ActivationMessage) -> None:
         rt = self.runtime
         if msg.dtype in (fr.SCHED_DTYPE, fr.LEASE_DTYPE):
@@ -167,40 +206,8 @@ class OffloadPolicy(ComputePolicy):
                     for lid in window_layers:
                         self.weight_cache.decrease_reference(lid, release_event=cc.release_event(rt))
 
-                    # eviction (reference offload.py:253-312)
                     try:
-                        if self._mode == "sliding_fit":
-                            if int(self._resident_windows) <= 1:
-                                if did_early_swap:
-                                    pass
-                                elif not self._recent_windows:
-                                    self._recent_windows.append(list(window_layers))
-                                else:
-                                    prev = self._recent_windows.pop(0)
-                                    self._delta_swap_eviction(window_layers, prev)
-                                    budget = max(1, int(self.window_size or 1))
-                                    curr = list(window_layers)
-                                    prev_only = [p for p in prev if p not in curr]
-                                    keep_quota = max(0, budget - len(curr))
-                                    keep_tail = prev_only[-keep_quota:] if keep_quota > 0 else []
-                                    self._recent_windows.append(list(keep_tail) + curr)
-                            else:
-                                self._recent_windows.append(list(window_layers))
-                        else:
-                            self._recent_windows.append(list(window_layers))
-                            if int(self._resident_windows) <= 1:
-                                old = self._recent_windows.pop(0)
-                                self.weight_cache.evict_layers(old)
-                                rt.model.unload_layers(old)
-                                for lid in old:
-                                    self._bound_versions.pop(lid, None)
-                            elif not self._defer_unload:
-                                while len(self._recent_windows) > max(1, int(self._resident_windows)):
-                                    old = self._recent_windows.pop(0)
-                                    self.weight_cache.evict_layers(old)
-                                    rt.model.unload_layers(old)
-                                    for lid in old:
-                                        self._bound_versions.pop(lid, None)
+                        self._retire_window(window_layers, did_early_swap)
                     except Exception:
                         pass
 
