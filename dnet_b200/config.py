@@ -51,6 +51,7 @@ class TransportSettings:  # reference config.py:108-127 (prefix DNET_TRANSPORT_)
     hop_bulk_tokens: int = field(default_factory=lambda: _env("DNET_TRANSPORT_HOP_BULK_TOKENS", 512, int))
     sched_rounds_per_frame: int = field(default_factory=lambda: _env("DNET_TRANSPORT_SCHED_ROUNDS", 4, int))
     sched_frames_in_flight: int = field(default_factory=lambda: _env("DNET_TRANSPORT_SCHED_DEPTH", 3, int))
+    lease_grace_s: float = field(default_factory=lambda: _env("DNET_TRANSPORT_LEASE_GRACE_S", 5e-4, float))
     # lm_head tensor-parallel over the ring during on-device decode: "auto" (rings of >= 4 shards), "on", "off"
     head_tp: str = field(default_factory=lambda: _env("DNET_TRANSPORT_HEAD_TP", "auto"))
     # extra schedule entries between a token's last layer and its head parts: 0 couples every shard to the last

@@ -100,6 +100,7 @@ class RingAdapter(TopologyAdapter):
         self.bulk_tokens = int(getattr(self.transport_settings, "hop_bulk_tokens", 512))
         self.rounds_per_frame = int(getattr(self.transport_settings, "sched_rounds_per_frame", 4))
         self.sched_depth = int(getattr(self.transport_settings, "sched_frames_in_flight", 3))
+        self.lease_grace_s = float(getattr(self.transport_settings, "lease_grace_s", 5e-4))
         self._leases: Dict[str, int] = {}                 # head: nonce -> decode steps still to schedule
         self._lease_evt: Optional[asyncio.Event] = None
         self._bulk_seq: Dict[int, int] = {}               # lane -> last bulk-flag value this shard sent
@@ -497,6 +498,9 @@ class RingAdapter(TopologyAdapter):
                 if not self._leases and not self._tp_flush:
                     self._lease_evt.clear()
                     await self._lease_evt.wait()
+                    # leases of concurrent requests arrive as separate frames within a few hundred microseconds: collect
+                    # them before fixing the order, or the first request would be scheduled alone (bubble-padded rounds)
+                    await asyncio.sleep(self.lease_grace_s)
                 if not self.is_head:
                     self._leases.clear()
                     continue
