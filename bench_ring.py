@@ -14,8 +14,10 @@ wait+step+hop kernel per (nonce, step)).  torch.distributed is plumbing only (ba
 max-over-ranks reduction of the device time); no collective is on the data path.
 
 Timed region (both numbers come from the SAME K steps):
-  value  CUDA events on every rank's compute stream around all kernels of the K steps x NS nonces,
-         max over ranks  (device time, includes every gap the host-side scheduling leaves)
+  value  CUDA events on every rank's compute stream from right before its first kernel of the K steps x NS
+         nonces to behind its last, max over ranks  (device time: pipeline fill and every gap the host-side
+         scheduling leaves between launches included; the lease / schedule-frame latency before the first launch
+         is not -- that is in e2e)
   e2e    wall clock on the API rank from submitting the leases to holding the last token on the host
          (per step and nonce: 8 bytes device->host through the pinned token ring; host->device: the
          schedule frame entries, 8 bytes per (nonce, step))
@@ -180,7 +182,9 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         stream.synchronize()
         torch.cuda.synchronize()
         barrier()
-        e0.record(stream)
+        # e0 is recorded by the policy on the compute stream right before this rank launches its first kernel of the
+        # window (device time of the K steps; the control plane's latency -- lease, schedule, frame -- is in `e2e`)
+        pol.sched_marks[base_entries] = e0
         t0 = time.perf_counter()
         if on_api:
             lease_all(steps)
@@ -196,6 +200,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         stream.synchronize()
         torch.cuda.synchronize()
         barrier()
+        run_steps.t_lease = t0
         return e0.elapsed_time(e1), wall
 
     # ---- warm-up, then the timed K steps
@@ -235,7 +240,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
         ts_ = stamps[stamp0:stamp0 + K * NS]
         if len(ts_) >= 20:
             a, b = len(ts_) // 10, len(ts_) - len(ts_) // 10 - 1
-            steady = {"tok_s_middle_80pct": (b - a) / (ts_[b] - ts_[a]), "first_token_ms_after_lease": (ts_[0] - tw0) * 1e3,
+            steady = {"tok_s_middle_80pct": (b - a) / (ts_[b] - ts_[a]), "first_token_ms_after_lease": (ts_[0] - run_steps.t_lease) * 1e3,
                       "note": "host arrival times of the timed tokens: rate between the 10 % and 90 % marks, and how long after "
                               "submitting the leases the first token arrived (lease -> schedule frames round the ring -> pipeline fill)"}
     steady_v = allmax(steady["tok_s_middle_80pct"] if steady else 0.0)

@@ -31,6 +31,8 @@ class FitInMemoryPolicy(ComputePolicy):
         self._mode = "fit"
         self._run_arrays = {}            # tuple(run) -> ctypes int32 array handed to dn_shard_step
         self.sched_entries_done = 0      # decode steps launched from schedule frames (progress signal for drivers)
+        self.sched_marks = {}            # real-entry count -> torch.cuda.Event recorded on the compute stream right BEFORE
+                                         # the entry with that index is launched (drivers time a window of entries with it)
         self.sched_host_s = 0.0          # host seconds spent inside _process_sched, and the entries it covered
         self.sched_host_entries = 0
         from collections import deque
@@ -146,6 +148,8 @@ class FitInMemoryPolicy(ComputePolicy):
                     tok_ptr = lp_ptr = None
                     if last:
                         tok_ptr, lp_ptr = rt.token_tap.post(lane, (nonce, seq, ns.params))
+                    if self.sched_marks:
+                        self._hit_mark()
                     _cabi.check(lib.dn_shard_step_hop(
                         rt.model._h, arr, len(run), ns.x1.data_ptr() if first else hop.rx.slot(lane), ns.kv._h,
                         1 if first else 0, 1 if last else 0, tok_ptr, lp_ptr, 1,
@@ -172,6 +176,11 @@ class FitInMemoryPolicy(ComputePolicy):
                 except Exception:
                     ev = None
                 ticket.record(ev)
+
+    def _hit_mark(self) -> None:
+        ev = self.sched_marks.pop(self.sched_entries_done, None)
+        if ev is not None:
+            ev.record(self.runtime.compute_stream)
 
     def _launch_sched_tp(self, entries, run, arr, first: bool, last: bool) -> None:
         """Schedule entries with the lm_head tensor-parallel over the ring.
@@ -229,6 +238,8 @@ class FitInMemoryPolicy(ComputePolicy):
             if ns is None:
                 logger.error("schedule entry for lane %d: no request holds that lane on shard %s", lane, rt.shard_id)
                 continue
+            if self.sched_marks:
+                self._hit_mark()
             if last:
                 tp.bc_n, tp.bc_seq = S, seq
                 for d in range(S):
