@@ -7,9 +7,10 @@ layer records (1.71 GB each) live in pinned host memory and each token swaps eve
 stream while the compute stream runs the resident window (OffloadPolicy + WeightCache + LayerManager +
 dn_slot_prefetch).  Activations hop between the two shards over NVLink (metadata-only frames); the token loop is the
 reference's host-closed loop (the API sends every token), because a shard that swaps layers cannot run the
-persistent step kernel.  Reported: decode tok/s (CUDA events per rank, max over ranks; and wall clock at the API),
-host->HBM GB/s per GPU against the box's own pinned-copy rate measured in the same run, and how much of a token's
-time the compute stream spent waiting for copies."""
+persistent step kernel.  Reported: decode tok/s over K tokens by the API's wall clock (the host closes the loop here,
+so the host IS on the token's critical path; there is no device-only interval that spans a token), host->HBM GB/s
+against the box's own pinned-copy rate measured in the same run, and the share of a token not covered by the
+compute the layers would need if they were resident."""
 from __future__ import annotations
 
 import json
@@ -90,20 +91,25 @@ def run_swap(args, rank: int, local_rank: int, world: int) -> None:
         f"HBM slots {pol.weight_cache.max_weights} x {layer_bytes / 1e9:.2f} GB; pinned copy rate {pcie:.1f} GB/s")
     barrier()
 
-    last = rank == world - 1
+    # the API sits beside the head shard (rank 0); the finalising shard returns tokens in process when it is the same
+    # process, else over the reference's own SendToken RPC (shardapi proto)
+    on_api = rank == 0
     got = []
     api = None
-    if last:
-        api = ApiNode(f"127.0.0.1:{ports[0]}", callback="local://")
-        node.adapter.token_sink = api.token_sink
+    if on_api:
+        api_port = base_port + 7 * world + 3
+        if world == 1:
+            api = ApiNode(f"127.0.0.1:{ports[0]}", callback="local://")
+            node.adapter.token_sink = api.token_sink
+        else:
+            api = ApiNode(f"127.0.0.1:{ports[0]}", callback="grpc", grpc_port=api_port)
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(0, cfg["vocab_size"], (B.PROMPT_LEN,), generator=g).tolist()
     stream = rt.compute_stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     wall = 0.0
     tw0 = tw1 = time.perf_counter()
-    if last:
+    if on_api:
         async def run():
             nonlocal wall, tw0, tw1
             i = 0
@@ -114,15 +120,14 @@ def run_swap(args, rank: int, local_rank: int, world: int) -> None:
                     tw0 = time.perf_counter()
             tw1 = time.perf_counter()
             wall = tw1 - tw0
-        if rank == 0:
-            sampler.start()
+        sampler.start()
         api.call(run(), timeout=3600)
     # ranks that do not host the API just serve; completion is signalled by the barrier below
     barrier()
     stream.synchronize()
     # per-rank accounting: every local layer is swapped in once per token
     lm = pol.weight_cache.layer_manager
-    ms_tok = wall / K * 1e3 if last else 0.0
+    ms_tok = wall / K * 1e3 if on_api else 0.0
     if gloo is not None:
         t = torch.tensor([ms_tok], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=gloo)
@@ -138,7 +143,8 @@ def run_swap(args, rank: int, local_rank: int, world: int) -> None:
                                       f"window {W} x resident windows {args.swap_resident_windows} -> {pol.weight_cache.max_weights} HBM layer slots "
                                       f"of {layer_bytes / 1e9:.2f} GB per shard, every layer swapped in from pinned host memory each token "
                                       f"(policy '{pol._mode}')", "prompt_len": B.PROMPT_LEN, "wire_dtype": "bf16", "kv": "fp16 paged",
-                          "token_loop": "host-closed (API sends every token); activations hop over NVLink as metadata-only frames"},
+                          "token_loop": "host-closed (API sends every token); activations hop over NVLink as metadata-only frames",
+                          "timing": "wall clock at the API over K tokens after W warm-up tokens (host-closed loop)"},
                "e2e": {"value": 1e3 / ms_tok, "unit": "tok/s", "h2d_bytes_per_step": world * len(mine) * layer_bytes + 4,
                        "d2h_bytes_per_step": 8, "api": "InferenceManager.generate_stream(device_loop=False) over the ring transport"},
                "gpu_launches": int(lib.dn_launch_count()),

@@ -32,13 +32,18 @@ class InferenceManager:
     async def generate_stream(self, nonce: str, prompt_ids: Sequence[int], max_tokens: int, *,
                               decoding: Optional[DecodingConfig] = None, stop_ids: Iterable[int] = (),
                               logprobs: bool = False, device_loop: bool = True, lease_steps: int = 16,
-                              lease_ahead: int = 8) -> AsyncIterator[TokenResult]:
+                              lease_ahead: int = 8, prefill_chunk: int = 0) -> AsyncIterator[TokenResult]:
         stop = set(int(t) for t in stop_ids)
         ad = self.adapter
         dec = decoding or DecodingConfig(temperature=0.0)
         device_loop = device_loop and float(dec.temperature) == 0.0     # the fused step samples greedily
-        await ad.send_tokens(nonce, np.asarray(list(prompt_ids), np.int32).tobytes(), self.callback_addr,
-                             logprobs=logprobs, decoding_config=dec)
+        ids = np.asarray(list(prompt_ids), np.int32)
+        step = int(prefill_chunk) if prefill_chunk and prefill_chunk > 0 else max(1, len(ids))
+        # chunked prefill: the chunks stream through the ring back to back (shard r works on chunk k while
+        # shard r+1 works on chunk k-1); only the last one is sampled
+        for c0 in range(0, max(1, len(ids)), step):
+            await ad.send_tokens(nonce, ids[c0:c0 + step].tobytes(), self.callback_addr, logprobs=logprobs,
+                                 decoding_config=dec, more=c0 + step < len(ids))
         produced = 0
         leased = 0
         try:

@@ -85,10 +85,10 @@ class RingApiAdapter:
         ctx.touch()
 
     def _request(self, nonce: str, dtype: str, data: bytes, callback_addr: str, logprobs: bool, top_logprobs: int,
-                 decoding_config: Optional[Any]):
+                 decoding_config: Optional[Any], more: bool = False):
         d = decoding_config
         msg = ActivationMessage(
-            nonce=nonce, pool_id=-1, batch_size=1, shape=(1,), dtype=dtype, layer_id=-1, timestamp=utc_epoch_now(),
+            nonce=nonce, pool_id=-1, batch_size=0 if more else 1, shape=(1,), dtype=dtype, layer_id=-1, timestamp=utc_epoch_now(),
             node_origin="api", callback_url=callback_addr if "://" in callback_addr else f"grpc://{callback_addr}",
             req_logprobs=logprobs, req_top_logprobs=top_logprobs,
             temperature=d.temperature if d else 1.0, top_p=d.top_p if d else 1.0, top_k=d.top_k if d else -1,
@@ -97,9 +97,12 @@ class RingApiAdapter:
         return msg.to_proto(data)
 
     async def send_tokens(self, nonce: str, tokens: bytes, callback_addr: str, logprobs: bool = False,
-                          top_logprobs: int = 0, decoding_config: Optional[Any] = None) -> None:
-        """int32 token ids (prompt, or one sampled token in the host-closed loop) to the first shard."""
-        await self._put(nonce, self._request(nonce, "tokens", tokens, callback_addr, logprobs, top_logprobs, decoding_config))
+                          top_logprobs: int = 0, decoding_config: Optional[Any] = None, more: bool = False) -> None:
+        """int32 token ids (prompt, or one sampled token in the host-closed loop) to the first shard.
+        ``more=True`` marks a prompt chunk that is not the last (chunked prefill): the ring fills the KV cache
+        and returns no token for it."""
+        await self._put(nonce, self._request(nonce, "tokens", tokens, callback_addr, logprobs, top_logprobs,
+                                             decoding_config, more=more))
 
     async def lease(self, nonce: str, steps: int, callback_addr: str = "", token: Optional[int] = None) -> None:
         """Let the ring decode ``steps`` more tokens of ``nonce`` with the token loop closed on the device."""

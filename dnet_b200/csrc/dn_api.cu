@@ -45,6 +45,7 @@ static int g_inflight_hi = 3;   // step kernel: cap while the consumers are star
 static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
 static int g_inflight = 2;      // step kernel: ring stages with loads outstanding while the consumers are not starving (barriers, staging); measured caps 2/3/4/5/none = 357/381/374/369/366 tok/s static, 2-when-idle/3-when-starving +0.7 % on top
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
+static int g_attn_single = 768; // step kernel: up to this context one CTA per head runs several tile passes instead of splitting the head
 static int g_attn_tc = 1;       // step kernel: tensor-core attention phase (shared-memory K/V tiles + mma) for long contexts ...
 static int g_attn_tc_min = 12288;   // ... from this many tokens of context on (bf16 KV)
 static int g_mk_debug = 0;
@@ -248,7 +249,9 @@ static cudaError_t init_kernel_attrs() {
 #define PRE(k) if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
   PRE(k_hop_send) PRE(k_flag_set) PRE(k_flag_wait) PRE(k_embed) PRE(k_advance) PRE(k_set_state)
   PRE(k_attn<1>) PRE(k_attn<2>) PRE(k_attn<4>) PRE(k_attn<5>) PRE(k_attn<7>) PRE(k_attn<8>)
-  PRE(k_shard_step<1>) PRE(k_shard_step<2>) PRE(k_shard_step<4>) PRE(k_shard_step<5>) PRE(k_shard_step<7>) PRE(k_shard_step<8>)
+#define PRS(Gv) PRE((k_shard_step<Gv, MK_ATT_PLAIN>)) PRE((k_shard_step<Gv, MK_ATT_TC>)) PRE((k_shard_step<Gv, MK_ATT_Q8>)) PRE((k_shard_step<Gv, MK_ATT_Q4>))
+  PRS(1) PRS(2) PRS(4) PRS(5) PRS(7) PRS(8)
+#undef PRS
 #undef PRE
 #define ATA(Gv) if ((e = cudaFuncSetAttribute(k_attn_prefill_tc<Gv>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)) != cudaSuccess) return e;
   ATA(1) ATA(2) ATA(4) ATA(8)
@@ -285,6 +288,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "tc_prefill")) { g_tc_prefill = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "gemm_bn256")) { g_gemm_bn256 = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "tc_attn")) { g_tc_attn = value ? 1 : 0; return DN_OK; }
+  if (!strcmp(key, "attn_single")) { g_attn_single = (int)value; return DN_OK; }
   if (!strcmp(key, "attn_tc")) { g_attn_tc = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "attn_tc_min")) { g_attn_tc_min = (int)value; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
@@ -851,14 +855,14 @@ extern "C" int dn_head_logits(dn_model* m, const void* x, int T, float* logits_f
 // ---------------------------------------------------------------------------------
 // the single-token shard step as one persistent kernel (dn_megakernel.cuh)
 // ---------------------------------------------------------------------------------
-static int g_mk_smem_set = 0;
-template <int G>
-static cudaError_t launch_step(const MkParams& p, size_t smem, cudaStream_t s) {
+static int g_mk_smem_set[4] = {0, 0, 0, 0};
+template <int G, int MODE>
+static cudaError_t launch_step_mode(const MkParams& p, size_t smem, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
-  if (!(g_mk_smem_set & (1 << G))) {
-    e = cudaFuncSetAttribute(k_shard_step<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (!(g_mk_smem_set[MODE] & (1 << G))) {
+    e = cudaFuncSetAttribute(k_shard_step<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    g_mk_smem_set |= (1 << G);
+    g_mk_smem_set[MODE] |= (1 << G);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -873,7 +877,16 @@ static cudaError_t launch_step(const MkParams& p, size_t smem, cudaStream_t s) {
   cfg.numAttrs = 1;
   if (g_capturing) g_capture_launches++;
   else g_launches++;
-  return cudaLaunchKernelEx(&cfg, k_shard_step<G>, p);
+  return cudaLaunchKernelEx(&cfg, k_shard_step<G, MODE>, p);
+}
+// one instantiation per attention form (dn_megakernel.cuh MK_ATT_*): the launch picks it from the same two fields
+// the kernel used to branch on
+template <int G>
+static cudaError_t launch_step(const MkParams& p, size_t smem, cudaStream_t s) {
+  if (p.kv_bits == 8) return launch_step_mode<G, MK_ATT_Q8>(p, smem, s);
+  if (p.kv_bits == 4) return launch_step_mode<G, MK_ATT_Q4>(p, smem, s);
+  if (p.attn_tc) return launch_step_mode<G, MK_ATT_TC>(p, smem, s);
+  return launch_step_mode<G, MK_ATT_PLAIN>(p, smem, s);
 }
 
 struct HopArgs {
@@ -951,6 +964,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.bar_count = m->mk_sync; p.bar_epoch = m->mk_sync + 1; p.err = m->mk_sync + 2;
   p.pf_depth = g_pf_depth;
   p.attn_chunk = g_attn_chunk;
+  p.attn_single = g_attn_single;
   p.inflight = g_inflight;
   p.inflight_hi = g_inflight_hi > g_inflight ? g_inflight_hi : g_inflight;
   // TMEM parking needs one fragment geometry (seg == 1024) in every phase

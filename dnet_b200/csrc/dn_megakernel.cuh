@@ -99,6 +99,7 @@ struct MkParams {
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
   int attn_tc;               // 1: long-context attention phase on mma.sync with K/V tiles staged in shared memory (mk_attention_tc)
+  int attn_single;           // plain attention: contexts up to this many tokens keep one CTA per head (no split merge)
   // quantised KV (dn_kvquant.cuh): 0 = bf16 pages; 4 / 8 = packed pages, two-pass attention
   int kv_bits;
   bf16* kv_stage;            // bf16 staging pool the q/k/v epilogue writes the new K/V row into
@@ -665,6 +666,13 @@ __device__ __forceinline__ void mk_stage_rmsnorm(bf16* xs, float* scratch, const
 // split's tiles round-robin, merging through shared memory.  A second CTA split per head is only
 // added once every warp already has `attn_chunk` tokens, so short contexts need no cross-CTA
 // merge at all (S == 1: the CTA writes the normalised head output directly).
+// The attention phase exists in four forms; the step kernel is instantiated once per form (template MODE) so that the
+// common one (16-bit KV, short/medium contexts) carries none of the others' code: measured, the all-in-one kernel was
+// 0.5 % slower at a 128-token context for that alone.
+constexpr int MK_ATT_PLAIN = 0;   // 16-bit pages, CUDA-core tiles straight from global memory
+constexpr int MK_ATT_TC = 1;      // 16-bit pages, long contexts: shared-memory tiles + mma.sync for the GQA group
+constexpr int MK_ATT_Q8 = 2;      // 8-bit affine-quantised pages, two-pass
+constexpr int MK_ATT_Q4 = 3;      // 4-bit
 constexpr int ATC_TOK = 16;                           // tokens per warp tile of the tensor-core attention
 constexpr int ATC_PITCH = HD * 2 + 16;                // 272-byte rows: the 8 row addresses of an ldmatrix hit 8 different bank groups
 constexpr int ATC_TILE_BYTES = ATC_TOK * ATC_PITCH;   // 4,352
@@ -685,6 +693,13 @@ __device__ __forceinline__ void mk_attn_geometry(const MkParams& p, int kv_len, 
     return;
   }
   const int n_tiles = (kv_len + 31) >> 5;
+  if (n_tiles <= (p.attn_single >> 5)) {
+    // short contexts: ONE CTA per head even when its warps need a second or third tile -- splitting a head over CTAs
+    // costs the merge while staging o_proj (measured 3.5 us per layer against 0.85 us for the plain copy), an extra
+    // tile pass costs ~1 us
+    S = 1; tps = n_tiles;
+    return;
+  }
   int smax = (int)gridDim.x / p.n_heads;
   smax = max(1, min(smax, min(p.nsplit, 8)));
   const int per_cta = MK_CW * max(1, p.attn_chunk >> 5);
@@ -1162,15 +1177,16 @@ __device__ __forceinline__ void mk_attention_q(const MkParams& p, const MkLayer&
 // o_proj staging = merge of the attention splits (fixed order -> deterministic) straight into the
 // shared activation vector: every CTA does it redundantly from L2 (nact x 132 floats per head),
 // which removes the ticket + last-CTA merge + one more round trip from the critical path.
+template <int MODE>
 __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p) {
   const int kv_len = p.st->pos + 1;
   int nact, tps;
   mk_attn_geometry(p, kv_len, nact, tps);
-  if (nact == 1 || p.attn_tc) {          // the attention CTAs already wrote the normalised heads
+  if (nact == 1 || MODE == MK_ATT_TC) {  // the attention CTAs already wrote the normalised heads
     mk_stage_copy(xs, p.attn, p.n_heads * HD);
     return;
   }
-  if (p.kv_bits != 0) {
+  if (MODE == MK_ATT_Q8 || MODE == MK_ATT_Q4) {
     // quantised KV: every split's partial is already normalised by the head's global (max, sum): out = bf16(sum of partials)
     for (int i = threadIdx.x; i < p.n_heads * 32; i += MK_CTHREADS) {
       const int head = i >> 5, l4 = i & 31;
@@ -1254,8 +1270,9 @@ __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p)
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-template <int G>
+template <int G, int MODE>
 __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) {
+  constexpr bool QUANT = MODE == MK_ATT_Q8 || MODE == MK_ATT_Q4;
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [ring n_stages*16K][scratch scratch_bytes][full[12]][empty[12]][red floats]
   MkRing ring;
@@ -1420,9 +1437,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
   int att_S, att_tps;
   mk_attn_geometry(p, pos + 1, att_S, att_tps);
   const int att_tile0 = ((int)blockIdx.x % att_S) * att_tps + cw;        // this warp's first tile (if the CTA has an attention task)
-  const bool att_has = p.kv_bits == 0 && !p.attn_tc && (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
+  const bool att_has = MODE == MK_ATT_PLAIN && (int)blockIdx.x < p.n_heads * att_S && att_tile0 < min((pos + 32) >> 5, ((int)blockIdx.x % att_S + 1) * att_tps);
   // quantised KV: value of this CTA's head counter before any arrival of this launch (arrivals happen after the first grid barrier)
-  const unsigned int tk_base = (p.kv_bits != 0 && (int)blockIdx.x < p.n_heads * att_S) ? __ldcg(p.head_tk + (int)blockIdx.x / att_S) : 0u;
+  const unsigned int tk_base = (QUANT && (int)blockIdx.x < p.n_heads * att_S) ? __ldcg(p.head_tk + (int)blockIdx.x / att_S) : 0u;
   const int att_phys0 = att_has ? p.block_table[(att_tile0 << 5) / PAGE] : 0;
   cbar_sync();
   const int tok_in = p.token_in != nullptr ? __ldcg(p.token_in) : p.st->token;
@@ -1470,8 +1487,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
         p.qbuf[hrow * HD + dim] = __float2bfloat16_rn(o);
       } else {
         // quantised KV: the bf16 row goes to the staging pool; the attention phase quantises and appends it
-        bf16* wpool = p.kv_bits ? p.kv_stage : L.kv_pool;
-        const int wpage = p.kv_bits ? (pos / PAGE) % KVQ_STAGE_PAGES : page_pos;
+        bf16* wpool = QUANT ? p.kv_stage : L.kv_pool;
+        const int wpage = QUANT ? (pos / PAGE) % KVQ_STAGE_PAGES : page_pos;
         const size_t off = (((size_t)wpage * 2 + (kind - 1)) * p.n_kv + hrow) * (PAGE * HD) + (size_t)(pos % PAGE) * HD + dim;
         wpool[off] = __float2bfloat16_rn(o);
       }
@@ -1481,16 +1498,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) k_shard_step(const MkParams p) 
     MK_STAMP(3);
 
     // ---- P2: paged-KV attention (split over pages; splits are merged while staging P3)
-    if (p.kv_bits == 8) mk_attention_q<G, 8>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
-    else if (p.kv_bits == 4) mk_attention_q<G, 4>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
-    else if (p.attn_tc) mk_attention_tc<G>(p, L, scratch, cw, lane, att_S, att_tps, ring, cs, reinterpret_cast<unsigned int*>(red + 61));
+    if constexpr (MODE == MK_ATT_Q8) mk_attention_q<G, 8>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
+    else if constexpr (MODE == MK_ATT_Q4) mk_attention_q<G, 4>(p, L, scratch, cw, lane, att_S, att_tps, li, tk_base);
+    else if constexpr (MODE == MK_ATT_TC) mk_attention_tc<G>(p, L, scratch, cw, lane, att_S, att_tps, ring, cs, reinterpret_cast<unsigned int*>(red + 61));
     else mk_attention<G>(p, L, scratch, cw, lane, att_S, att_tps, att_tile0, att_phys0);
     MK_STAMP(4);
     mk_grid_barrier(p, bar_k, ring, cs, bar_req, bar_done, lane);
     MK_STAMP(5);
 
     // ---- P3: merge attention splits -> o_proj + residual
-    mk_stage_attn_merge(xs, p);
+    mk_stage_attn_merge<MODE>(xs, p);
     MK_STAMP(6);
     mk_consume(p, PH_O, li, ring, xs, red2, cw, lane, consumed, cs, nblk,
                [&](int vr, bool owner) -> unsigned short { return (MK_OPT_PRE && owner) ? __ldcg(reinterpret_cast<const unsigned short*>(cur) + vr) : (unsigned short)0; },

@@ -73,7 +73,8 @@ class ActivationCodec:
         if pid is None:
             raise MemoryError("input pool exhausted")
         self.runtime.input_pool.get_buffer(pid)[:n] = torch.tensor(ids, dtype=torch.int32)
-        return ActivationMessage(nonce=nonce, pool_id=pid, batch_size=1, shape=(n,), dtype="tokens", layer_id=-1,
+        more = bool(kw.pop("more", False))     # an intermediate chunk of a chunked prefill (policies/_cuda_common.py)
+        return ActivationMessage(nonce=nonce, pool_id=pid, batch_size=0 if more else 1, shape=(n,), dtype="tokens", layer_id=-1,
                                  timestamp=0, node_origin=kw.pop("node_origin", "api"),
                                  callback_url=kw.pop("callback_url", "grpc://api:0"),
                                  temperature=kw.pop("temperature", 0.0), **kw)

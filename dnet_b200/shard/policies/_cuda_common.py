@@ -39,6 +39,14 @@ def local_run(rt, current_layer: int) -> List[int]:
     return run
 
 
+def more_chunks_follow(msg: ActivationMessage) -> bool:
+    """Chunked prefill: a prompt sent as several ``tokens`` frames.  Every frame but
+    the last carries ``Activation.batch_size == 0`` (the reference always sends 1 and never reads the field on
+    a shard, api/strategies/ring.py:74-140); the flag travels with the activation round the ring
+    (build_output copies it), and the finalising shard samples only after the chunk that has it clear."""
+    return int(getattr(msg, "batch_size", 1)) == 0
+
+
 def note_lane(rt, msg: ActivationMessage, ns) -> None:
     """Remember which hop lane the nonce rides (device-hop transport; set by the adapter's ingress)."""
     if msg.lane >= 0 and ns.lane != msg.lane:

@@ -299,6 +299,7 @@ class FitInMemoryPolicy(ComputePolicy):
                 last_layer = run[-1]
                 is_end = last_layer + 1 >= rt.model_metadata.num_layers
                 greedy = msg.temperature == 0 and msg.req_top_logprobs <= 0
+                more = cc.more_chunks_follow(msg)      # a prompt chunk that is not the last: fill the KV, sample nothing
 
                 # 2) bind (fast exit when everything is already bound)
                 to_bind = self._bind_layer_weights(run, msg)
@@ -329,9 +330,9 @@ class FitInMemoryPolicy(ComputePolicy):
                             logger.error("Failed to get input buffer %s", msg.pool_id)
                             return
                         x = staged[0]
-                    self._graph_step(ns, x, is_tokens, run, is_end and greedy)
+                    self._graph_step(ns, x, is_tokens, run, is_end and greedy and not more)
                     self.weight_cache.decrease_references(run)
-                    if is_end and greedy:
+                    if is_end and greedy and not more:
                         rt.compute_stream.synchronize()
                         if int(ns.result_np_i32[0]) <= -1000:
                             # a bounded in-kernel wait timed out: the step's results are invalid (sticky until cleared)
@@ -357,6 +358,9 @@ class FitInMemoryPolicy(ComputePolicy):
                             self.weight_cache.decrease_reference(lid)
                     if last_layer == rt._assigned_sorted[-1]:
                         ns.kv.advance(T, rt.compute_stream_ptr)
+                if is_end and more:
+                    cc.finish_input(rt, msg, ns)       # the last shard swallows an intermediate prompt chunk
+                    return
                 if is_end and final is None:
                     try:
                         final = cc.sample_end_shard(rt, msg, ns, x)

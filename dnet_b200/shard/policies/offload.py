@@ -226,16 +226,20 @@ class OffloadPolicy(ComputePolicy):
                 if last_layer == rt._assigned_sorted[-1]:   # once per token even with k>1 rounds
                     ns.kv.advance(T, rt.compute_stream_ptr)
                 final = None
-                if last_layer + 1 >= rt.model_metadata.num_layers:
+                is_end = last_layer + 1 >= rt.model_metadata.num_layers
+                if is_end and not cc.more_chunks_follow(msg):
                     try:
                         final = cc.sample_end_shard(rt, msg, ns, x)
                     except Exception as e:
                         logger.error("End-shard sampling failed: %s", e)
                         rt.input_pool.release(msg.pool_id)
                         return
-                output_msg = cc.build_output(rt, msg, x, last_layer, final)
-                rt.emit_result(output_msg)
-                cc.finish_input(rt, msg, ns)
+                if is_end and final is None:
+                    cc.finish_input(rt, msg, ns)       # intermediate prompt chunk on the last shard: nothing to emit
+                else:
+                    output_msg = cc.build_output(rt, msg, x, last_layer, final)
+                    rt.emit_result(output_msg)
+                    cc.finish_input(rt, msg, ns)
 
                 # schedule prefetch of the next local window, or wrap to the first window so the
                 # next token's first copies overlap the other shards' compute

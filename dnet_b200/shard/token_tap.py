@@ -90,8 +90,10 @@ class TokenTap:
 
     def _run(self) -> None:
         # Never spin: this thread shares the GIL with the compute thread that launches the step kernels, and a
-        # Python busy loop here delays those launches (measured at 8 shards: ~50 us per slot on the finalising shard).
-        # A 50 us nap between polls costs a token 25 us of observation latency on average and nothing else.
+        # Python busy loop here competes with those launches for the interpreter (the 8-shard ring went from
+        # 2,268 to 2,937 tok/s over the set of changes that included replacing the spin with this nap; the
+        # nap's own share was not isolated).  A 50 us nap between polls costs a token ~25 us of observation
+        # latency on average and nothing on the device.
         while self._running:
             self.poll_once()
             if self.in_flight() == 0:

@@ -99,6 +99,10 @@ def test_many_nonces_in_flight_do_not_disturb_each_other(tiny):
         many = api.generate_many(prompts, 10, prefix="many", device_loop=True, lease_steps=3, lease_ahead=1)
         assert [[r.token_id for r in seq] for seq in many] == solo
         assert solo[0] == [int(t) for t in g["tokens"][:10]]
+        # the end_of_request frames are processed by the shard after the API's generate returns
+        t0 = time.time()
+        while node.adapter._streams.lanes_in_use() and time.time() - t0 < 5.0:
+            time.sleep(0.01)
         lanes = node.adapter._streams.lanes_in_use()
         assert not lanes, f"every request ended: no lane may stay claimed, got {lanes}"
     finally:
@@ -149,6 +153,12 @@ def test_two_shards_one_process_activations_travel_as_device_hops(tiny):
         long_prompt = torch.randint(0, cfgd["vocab_size"], (n0.adapter.bulk_tokens + 8,), generator=torch.Generator().manual_seed(3)).tolist()
         out2 = api.generate("long", long_prompt, 3, device_loop=False)
         assert len(out2) == 3 and n0.adapter.stats["frames_bytes"] == 1
+        # chunked prefill: the same prompt as 64-token chunks (every chunk a device hop, only the last one sampled)
+        hops_before = n0.adapter.stats["frames_hop"]
+        out3 = api.generate("chunked", long_prompt, 3, device_loop=False, prefill_chunk=64)
+        assert [r.token_id for r in out3] == [r.token_id for r in out2]
+        n_chunks = -(-len(long_prompt) // 64)
+        assert n0.adapter.stats["frames_hop"] - hops_before == n_chunks + 2 and n0.adapter.stats["frames_bytes"] == 1
     finally:
         if api is not None:
             api.shutdown()
