@@ -49,6 +49,7 @@ class ModelCfg(C.Structure):
         ("ffn", C.c_int32), ("vocab", C.c_int32), ("n_layers_total", C.c_int32), ("rms_eps", C.c_float),
         ("tie_embeddings", C.c_int32), ("dtype", C.c_int32), ("wire_dtype", C.c_int32),
         ("kv_page_tokens", C.c_int32), ("kv_pool_pages", C.c_int32), ("kv_bits", C.c_int32), ("kv_group", C.c_int32),
+        ("n_experts", C.c_int32), ("top_k", C.c_int32),
     ]
 
 
@@ -82,6 +83,7 @@ _PROTOS = {
     "dn_model_create": (_i, [C.POINTER(ModelCfg), C.POINTER(C.c_int32), _i, C.POINTER(C.c_float), C.POINTER(_vp)]),
     "dn_model_destroy": (_i, [_vp]),
     "dn_bind_layer": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "dn_bind_layer_experts": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i]),
     "dn_unbind_layer": (_i, [_vp, _i]),
     "dn_layer_is_bound": (_i, [_vp, _i]),
     "dn_bind_api": (_i, [_vp, _vp, _vp, _vp]),

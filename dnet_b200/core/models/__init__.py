@@ -2,7 +2,7 @@
 from typing import Any, List, Optional
 
 from .base import BaseRingModel, KVHandle
-from .llama import LlamaRingModel, Qwen2RingModel
+from .llama import LlamaRingModel, MixtralRingModel, Qwen2RingModel
 
 
 def _subclasses(cls):
@@ -20,4 +20,4 @@ def get_ring_model(model_type: str, model_config: Any, assigned_layers: Optional
     raise ValueError(f"Unsupported model type: {model_type}")
 
 
-__all__ = ["BaseRingModel", "KVHandle", "LlamaRingModel", "Qwen2RingModel", "get_ring_model"]
+__all__ = ["BaseRingModel", "KVHandle", "LlamaRingModel", "MixtralRingModel", "Qwen2RingModel", "get_ring_model"]

@@ -118,8 +118,10 @@ class BaseRingModel(ABC):
             ffn=cfg["intermediate_size"], vocab=cfg["vocab_size"], n_layers_total=cfg["num_hidden_layers"],
             rms_eps=float(cfg.get("rms_norm_eps", 1e-5)), tie_embeddings=int(bool(cfg.get("tie_word_embeddings", False))),
             dtype=0, wire_dtype=0, kv_page_tokens=64, kv_pool_pages=int(kv_pool_pages), kv_bits=int(kv_bits),
-            kv_group=int(kv_group))
+            kv_group=int(kv_group), n_experts=int(cfg.get("num_local_experts", 0) or 0),
+            top_k=int(cfg.get("num_experts_per_tok", 0) or 0))
         self.kv_bits = int(kv_bits)
+        self.n_experts = int(mc.n_experts)
         layers = sorted(assigned_layers or [])
         arr = (C.c_int32 * max(1, len(layers)))(*layers)
         inv = inv_freq.to(torch.float32).contiguous().cpu()
@@ -211,6 +213,8 @@ class BaseRingModel(ABC):
                     raise ValueError(f"layer {abs_idx} {suffix}: expected a contiguous bf16 CUDA tensor")
                 ptrs[slot] = t.data_ptr()
             _cabi.check(self._lib.dn_bind_layer(self._h, abs_idx, ptrs))
+            if getattr(self, "n_experts", 0):
+                self._bind_experts(abs_idx, tensors)
             self._bound[abs_idx] = tensors  # keep the borrowed views alive
         if api_changed:
             e, n, hh = self._api.get("embed_tokens.weight"), self._api.get("norm.weight"), self._api.get("lm_head.weight")
@@ -221,6 +225,30 @@ class BaseRingModel(ABC):
                                               n.data_ptr() if n is not None else None,
                                               hh.data_ptr() if hh is not None else None))
         return self
+
+    # sparse MoE layers: HF / mlx_lm checkpoint names of the router and the experts (mixtral)
+    EXPERT_ROUTER = "block_sparse_moe.gate.weight"
+    EXPERT_FMT = "block_sparse_moe.experts.{e}.{w}.weight"       # w1 = gate, w3 = up, w2 = down
+
+    def _bind_experts(self, abs_idx: int, tensors: Dict[str, torch.Tensor]) -> None:
+        E = self.n_experts
+        router = tensors.get(self.EXPERT_ROUTER)
+        if router is None:
+            raise ValueError(f"layer {abs_idx}: MoE model without {self.EXPERT_ROUTER}")
+        tabs = []
+        for w in ("w1", "w3", "w2"):
+            arr = (C.c_void_p * E)()
+            for e in range(E):
+                t = tensors.get(self.EXPERT_FMT.format(e=e, w=w))
+                if t is None:
+                    raise ValueError(f"layer {abs_idx}: expert {e} has no {w}")
+                if not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
+                    raise ValueError(f"layer {abs_idx} expert {e} {w}: expected a contiguous bf16 CUDA tensor")
+                arr[e] = t.data_ptr()
+            tabs.append(arr)
+        if not router.is_cuda or router.dtype != torch.bfloat16 or not router.is_contiguous():
+            raise ValueError(f"layer {abs_idx} router: expected a contiguous bf16 CUDA tensor")
+        _cabi.check(self._lib.dn_bind_layer_experts(self._h, abs_idx, router.data_ptr(), tabs[0], tabs[1], tabs[2], E))
 
     def unload_layers(self, abs_layers: List[int]) -> None:
         """Drop the binding of the given absolute layers (reference base.py:474-486 shrinks

@@ -129,3 +129,14 @@ class Qwen2RingModel(LlamaRingModel):
     wrapper, BASELINE config 3 needs one."""
 
     model_type = "qwen2"
+
+
+class MixtralRingModel(LlamaRingModel):
+    """mixtral = llama attention + a sparse MoE FFN (mlx_lm.models.mixtral: router -> top-k experts -> softmax over
+    the selected logits -> SwiGLU experts -> weighted sum).  The reference has no mixtral wrapper; it hosts its MoE
+    families (gpt_oss, deepseek_v2) through this same operator API, and BASELINE.json configs[4] names
+    Mixtral-8x7B.  Expert selection happens on the device, so MoE layers run on the per-op path
+    (dn_window_forward; CUDA-graph capturable), not in the persistent step kernel."""
+
+    model_type = "mixtral"
+    step_kernel_ok = False

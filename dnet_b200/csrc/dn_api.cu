@@ -45,7 +45,8 @@ static int g_inflight_hi = 3;   // step kernel: cap while the consumers are star
 static int g_park = 1;          // step kernel: park ready ring stages in tensor memory during grid barriers
 static int g_inflight = 2;      // step kernel: ring stages with loads outstanding while the consumers are not starving (barriers, staging); measured caps 2/3/4/5/none = 357/381/374/369/366 tok/s static, 2-when-idle/3-when-starving +0.7 % on top
 static int g_attn_chunk = 32;   // step kernel: tokens per warp before a head is split over a second CTA
-static int g_attn_single = 768; // step kernel: up to this context one CTA per head runs several tile passes instead of splitting the head
+static int g_attn_single = 512; // step kernel: up to this context one CTA per head runs several tile passes instead of splitting the head
+static int g_attn_last = 1;     // step kernel, plain attention with split heads: last-arriving CTA merges (0 = every CTA merges while staging)
 static int g_attn_tc = 1;       // step kernel: tensor-core attention phase (shared-memory K/V tiles + mma) for long contexts ...
 static int g_attn_tc_min = 12288;   // ... from this many tokens of context on (bf16 KV)
 static int g_mk_debug = 0;
@@ -103,6 +104,10 @@ struct LayerW {
   bool bound = false;
   CUtensorMap tm[7];          // TMA descriptors of q,k,v,o,gate,up,down ([rows, K] bf16, box 128 x 64, SWIZZLE_128B)
   bool tm_ok = false;
+  // sparse MoE layers (cfg.n_experts > 0): router [E][H] and a device table [3][E] of expert pointers (gate, up, down)
+  const bf16* router = nullptr;
+  const bf16** etable = nullptr;
+  bool experts_bound = false;
 };
 
 constexpr int TPF_MAX = 512;   // tokens per tensor-core prefill chunk (weights are streamed once per chunk)
@@ -147,6 +152,9 @@ struct dn_model {
   unsigned int* tickets = nullptr;       // [tmax * n_kv] attention + [1] head
   HeadPartial* head_part = nullptr;
   float* inv_freq = nullptr;
+  // sparse MoE scratch: router logits [E], selected experts [k] + scores [k], running weighted sum [H]
+  float* moe_logits = nullptr; int32_t* moe_sel = nullptr; float* moe_score = nullptr; float* moe_y = nullptr;
+  const bf16** moe_tables = nullptr;    // [local layers][3][E]
   StepState* null_state = nullptr;      // zeroed step state + block table for launches without a nonce (head-part only)
   int32_t* null_bt = nullptr;
   // paged KV pool: [local layer][page][2][n_kv][PAGE][HD]
@@ -241,13 +249,14 @@ static cudaError_t init_kernel_attrs() {
   SETA(1, OpOProj) SETA(2, OpOProj) SETA(4, OpOProj)
   SETA(1, OpGateUp) SETA(2, OpGateUp) SETA(4, OpGateUp)
   SETA(1, OpHead)
+  SETA(1, OpRouter) SETA(1, OpGateUpMoe) SETA(1, OpDownMoe)
 #undef SETA
   // CUDA loads kernels lazily; loading can need a context-wide sync, so the first launch of a
   // kernel issued while k_flag_wait is spinning would deadlock until its timeout.  Touch every
   // kernel once here.
   cudaFuncAttributes fa;
 #define PRE(k) if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
-  PRE(k_hop_send) PRE(k_flag_set) PRE(k_flag_wait) PRE(k_embed) PRE(k_advance) PRE(k_set_state)
+  PRE(k_moe_select) PRE(k_hop_send) PRE(k_flag_set) PRE(k_flag_wait) PRE(k_embed) PRE(k_advance) PRE(k_set_state)
   PRE(k_attn<1>) PRE(k_attn<2>) PRE(k_attn<4>) PRE(k_attn<5>) PRE(k_attn<7>) PRE(k_attn<8>)
 #define PRS(Gv) PRE((k_shard_step<Gv, MK_ATT_PLAIN>)) PRE((k_shard_step<Gv, MK_ATT_TC>)) PRE((k_shard_step<Gv, MK_ATT_Q8>)) PRE((k_shard_step<Gv, MK_ATT_Q4>))
   PRS(1) PRS(2) PRS(4) PRS(5) PRS(7) PRS(8)
@@ -289,6 +298,7 @@ extern "C" int dn_set_option(const char* key, int64_t value) {
   if (!strcmp(key, "gemm_bn256")) { g_gemm_bn256 = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "tc_attn")) { g_tc_attn = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "attn_single")) { g_attn_single = (int)value; return DN_OK; }
+  if (!strcmp(key, "attn_last")) { g_attn_last = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "attn_tc")) { g_attn_tc = value ? 1 : 0; return DN_OK; }
   if (!strcmp(key, "attn_tc_min")) { g_attn_tc_min = (int)value; return DN_OK; }
   if (!strcmp(key, "mk_debug")) { g_mk_debug = (int)value; return DN_OK; }
@@ -340,6 +350,19 @@ extern "C" int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layer
   CK(cudaMalloc(&m->attn, (size_t)tmax * qd * 2));
   CK(cudaMalloc(&m->act, (size_t)tmax * cfg->ffn * 2));
   CK(cudaMalloc(&m->logits_bf16, (size_t)cfg->vocab * 2));
+  if (cfg->n_experts > 0) {
+    if (cfg->n_experts > MOE_MAX_E || cfg->top_k < 1 || cfg->top_k > MOE_MAX_K || cfg->top_k > cfg->n_experts || tmax < cfg->top_k) {
+      dn_model_destroy(m);
+      return fail(DN_EINVAL, "MoE: %d experts / top-%d unsupported (at most %d experts, top-%d)", cfg->n_experts, cfg->top_k, MOE_MAX_E, MOE_MAX_K);
+    }
+    CK(cudaMalloc(&m->moe_logits, (size_t)cfg->n_experts * sizeof(float)));
+    CK(cudaMalloc(&m->moe_sel, (size_t)MOE_MAX_K * sizeof(int32_t)));
+    CK(cudaMalloc(&m->moe_score, (size_t)MOE_MAX_K * sizeof(float)));
+    CK(cudaMalloc(&m->moe_y, (size_t)H * sizeof(float)));
+    CK(cudaMalloc(&m->moe_tables, (size_t)(n_layers > 0 ? n_layers : 1) * 3 * cfg->n_experts * sizeof(void*)));
+    CK(util_fill0(m->moe_sel, MOE_MAX_K * sizeof(int32_t)));
+    for (int i = 0; i < n_layers; ++i) m->layers[i].etable = m->moe_tables + (size_t)i * 3 * cfg->n_experts;
+  }
   CK(cudaMalloc(&m->part, (size_t)tmax * cfg->n_heads * ns * PART_STRIDE * sizeof(float)));
   CK(cudaMalloc(&m->tickets, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
   CK(util_fill0(m->tickets, ((size_t)tmax * cfg->n_kv_heads + 4) * sizeof(unsigned int)));
@@ -426,6 +449,7 @@ extern "C" int dn_model_destroy(dn_model* m) {
   cudaFree(m->mk_bounds); cudaFree(m->pf_xn); cudaFree(m->pf_qkv); cudaFree(m->pf_q); cudaFree(m->pf_attn); cudaFree(m->pf_h); cudaFree(m->pf_act);
   cudaFree(m->mk_dbg); cudaFree(m->mk_dev); cudaFree(m->xa); cudaFree(m->xb); cudaFree(m->mk_sync);
   cudaFree(m->null_state); cudaFree(m->null_bt);
+  cudaFree(m->moe_logits); cudaFree(m->moe_sel); cudaFree(m->moe_score); cudaFree(m->moe_y); cudaFree(m->moe_tables);
   cudaFree(m->kvq_stage); cudaFree(m->kvq_stage_bt); cudaFree(m->kvq_scores); cudaFree(m->kvq_head_tk);
   delete m;
   return DN_OK;
@@ -442,7 +466,9 @@ extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_
   LayerW& L = m->layers[it->second];
   for (int i = 0; i < DN_W_COUNT; ++i) {
     L.w[i] = static_cast<const bf16*>(dev_ptrs[i]);
-    if (i <= DN_W_LN2 && L.w[i] == nullptr) return fail(DN_EINVAL, "layer %d: tensor %d is null", abs_layer, i);
+    const bool dense_mlp = i == DN_W_GATE || i == DN_W_UP || i == DN_W_DOWN;
+    if (i <= DN_W_LN2 && L.w[i] == nullptr && !(dense_mlp && m->cfg.n_experts > 0))
+      return fail(DN_EINVAL, "layer %d: tensor %d is null", abs_layer, i);
     if (((uintptr_t)L.w[i]) & 15) return fail(DN_EINVAL, "layer %d: tensor %d is not 16-byte aligned", abs_layer, i);
   }
   L.bound = true;
@@ -452,11 +478,34 @@ extern "C" int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_
     const int rows[7] = {qd, kd, kd, H, c.ffn, c.ffn, H};
     const int cols[7] = {H, H, H, qd, H, H, c.ffn};
     L.tm_ok = m->pf_ok;
-    for (int i = 0; i < 7 && L.tm_ok; ++i) L.tm_ok = make_tmap(&L.tm[i], L.w[i], rows[i], cols[i], TC_BM) == DN_OK;
+    const int n_tm = m->cfg.n_experts > 0 ? 4 : 7;       // MoE layers: the expert FFN runs token by token, no GEMM descriptors
+    for (int i = 0; i < n_tm && L.tm_ok; ++i) L.tm_ok = make_tmap(&L.tm[i], L.w[i], rows[i], cols[i], TC_BM) == DN_OK;
   }
   MkLayer& ML = m->mk_host[it->second];
   for (int i = 0; i < DN_W_COUNT; ++i) ML.w[i] = L.w[i];
   CK(util_h2d(m->mk_dev + it->second, &ML, sizeof(MkLayer)));
+  return DN_OK;
+}
+
+// MoE layers: the router and the experts' gate / up / down matrices ([ffn][H], [ffn][H], [H][ffn] each, any placement).
+// The pointer table is copied to the device here; dn_bind_layer binds the layer's attention tensors and norms.
+extern "C" int dn_bind_layer_experts(dn_model* m, int abs_layer, const void* router, const void* const* gate,
+                                     const void* const* up, const void* const* down, int n_experts) {
+  if (!m || !router || !gate || !up || !down) return fail(DN_EINVAL, "null argument");
+  if (m->cfg.n_experts <= 0 || n_experts != m->cfg.n_experts) return fail(DN_EINVAL, "model has %d experts, got %d", m->cfg.n_experts, n_experts);
+  auto it = m->abs2local.find(abs_layer);
+  if (it == m->abs2local.end()) return fail(DN_ENOENT, "layer %d not hosted on this model instance", abs_layer);
+  LayerW& L = m->layers[it->second];
+  std::vector<const void*> tab((size_t)3 * n_experts);
+  for (int e = 0; e < n_experts; ++e) {
+    tab[e] = gate[e]; tab[n_experts + e] = up[e]; tab[2 * n_experts + e] = down[e];
+    if (!gate[e] || !up[e] || !down[e]) return fail(DN_EINVAL, "layer %d: expert %d has a null matrix", abs_layer, e);
+    if ((((uintptr_t)gate[e]) | ((uintptr_t)up[e]) | ((uintptr_t)down[e])) & 15) return fail(DN_EINVAL, "layer %d: expert %d is not 16-byte aligned", abs_layer, e);
+  }
+  if (((uintptr_t)router) & 15) return fail(DN_EINVAL, "layer %d: router is not 16-byte aligned", abs_layer);
+  CK(util_h2d(L.etable, tab.data(), tab.size() * sizeof(void*)));
+  L.router = static_cast<const bf16*>(router);
+  L.experts_bound = true;
   return DN_OK;
 }
 
@@ -465,6 +514,7 @@ extern "C" int dn_unbind_layer(dn_model* m, int abs_layer) {
   auto it = m->abs2local.find(abs_layer);
   if (it == m->abs2local.end()) return fail(DN_ENOENT, "layer %d not hosted on this model instance", abs_layer);
   m->layers[it->second].bound = false;
+  m->layers[it->second].experts_bound = false;
   memset(m->mk_host[it->second].w, 0, sizeof(m->mk_host[it->second].w));
   memset(m->layers[it->second].w, 0, sizeof(m->layers[it->second].w));
   return DN_OK;
@@ -609,6 +659,33 @@ static int kvq_append_and_attend(dn_model* m, int li, const bf16* q, bf16* attn_
   return DN_OK;
 }
 
+// sparse MoE FFN of one layer, token by token (dn_kernels.cuh "Sparse MoE FFN"): h = post-attention residual [T][H],
+// out = T(h + moe(RMSNorm(h))) [T][H].  4 + 2k launches per token, all with device-side expert indirection.
+static int moe_ffn(dn_model* m, const LayerW& L, const bf16* h, bf16* out, int T, cudaStream_t s) {
+  const dn_model_cfg& c = m->cfg;
+  if (!L.experts_bound) return fail(DN_ENOENT, "MoE layer has no experts bound (dn_bind_layer_experts)");
+  const int H = c.hidden, E = c.n_experts, k = c.top_k;
+  for (int t = 0; t < T; ++t) {
+    OpRouter r;
+    r.K = H; r.nrows = E; r.x = h + (size_t)t * H; r.ln_w = L.w[DN_W_LN2]; r.w = L.router; r.logits = m->moe_logits; r.eps = c.rms_eps;
+    CK((launch_gemv<1, OpRouter>(r, E, s)));
+    CK(launch(k_moe_select, dim3(1), dim3(32), 0, s, false, (const float*)m->moe_logits, E, k, m->moe_sel, m->moe_score));
+    for (int j = 0; j < k; ++j) {
+      OpGateUpMoe g;
+      g.K = H; g.nrows = 2 * c.ffn; g.x = h + (size_t)t * H; g.ln_w = L.w[DN_W_LN2]; g.table = L.etable; g.sel = m->moe_sel;
+      g.j = j; g.E = E; g.act = m->act + (size_t)j * c.ffn; g.eps = c.rms_eps;
+      CK((launch_gemv<1, OpGateUpMoe>(g, c.ffn, s)));
+    }
+    for (int j = 0; j < k; ++j) {
+      OpDownMoe d;
+      d.K = c.ffn; d.nrows = H; d.a = m->act + (size_t)j * c.ffn; d.table = L.etable; d.sel = m->moe_sel; d.score = m->moe_score;
+      d.j = j; d.k = k; d.E = E; d.ybuf = m->moe_y; d.resid = h + (size_t)t * H; d.out = out + (size_t)t * H;
+      CK((launch_gemv<1, OpDownMoe>(d, H, s)));
+    }
+  }
+  return DN_OK;
+}
+
 static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, cudaStream_t s, cudaEvent_t* evs = nullptr) {
   auto it = m->abs2local.find(abs_layer);
   if (it == m->abs2local.end()) return fail(DN_ENOENT, "Layer %d not hosted on this model instance", abs_layer);
@@ -640,6 +717,12 @@ static int layer_forward(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* kv, 
   CK(launch_gemv_T(T, o, o.nrows, s));
   if (evs) CK(cudaEventRecord(evs[3], s));
 
+  if (c.n_experts > 0) {
+    const int rc = moe_ffn(m, L, m->hbuf, x, T, s);
+    if (rc) return rc;
+    if (evs) { CK(cudaEventRecord(evs[4], s)); CK(cudaEventRecord(evs[5], s)); }
+    return DN_OK;
+  }
   OpGateUp g;
   g.K = H; g.nrows = 2 * c.ffn; g.x = m->hbuf; g.ln_w = L.w[DN_W_LN2];
   g.wg = L.w[DN_W_GATE]; g.wu = L.w[DN_W_UP]; g.act = m->act; g.eps = c.rms_eps;
@@ -739,6 +822,7 @@ static int layer_forward_tc(dn_model* m, int abs_layer, bf16* x, int T, dn_kv* k
   }
   p.K = qd; p.N = H; p.Y = m->pf_h; p.ldy = H; p.col0 = 0; p.resid = x; p.ldr = H;
   CK(gemm_tc<EPI_RESID>(L.tm[3], L.tm[3], m->tm_attn, p, s));
+  if (c.n_experts > 0) return moe_ffn(m, L, m->pf_h, x, T, s);
   k_rmsnorm_rows<<<T, 256, 0, s>>>(m->pf_h, L.w[DN_W_LN2], m->pf_xn, H, c.rms_eps);
   g_launches++;
   p.K = H; p.N = c.ffn; p.Y = m->pf_act; p.ldy = c.ffn; p.resid = nullptr;
@@ -929,6 +1013,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   const dn_tp_args* tp = hop.tp;
   const bool bubble = tp != nullptr && n == 0;          // tensor-parallel head: a launch that only serves another nonce's head part
   if (!m || n < 0 || (n > 0 && !abs_layers)) return fail(DN_EINVAL, "bad argument");
+  if (m->cfg.n_experts > 0) return fail(DN_EINVAL, "MoE models run on the per-op path (dn_window_forward), not in the persistent step kernel");
   if (!bubble && (!x_inout || !kv)) return fail(DN_EINVAL, "bad argument");
   if (kv && kv->m != m) return fail(DN_EINVAL, "kv belongs to a different model");
   if (n == 0 && !do_head && !(tp && (tp->hp_x || tp->mg_n > 0))) return fail(DN_EINVAL, "nothing to do");
@@ -965,6 +1050,7 @@ static int shard_step_impl(dn_model* m, const int32_t* abs_layers, int n, void* 
   p.pf_depth = g_pf_depth;
   p.attn_chunk = g_attn_chunk;
   p.attn_single = g_attn_single;
+  p.attn_last = g_attn_last;
   p.inflight = g_inflight;
   p.inflight_hi = g_inflight_hi > g_inflight ? g_inflight_hi : g_inflight;
   // TMEM parking needs one fragment geometry (seg == 1024) in every phase

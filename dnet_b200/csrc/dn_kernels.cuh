@@ -384,6 +384,113 @@ struct OpGateUp {
 typedef OpOProj OpDown;  // identical dataflow: a=[T][ffn], w=[H][ffn], resid=h, out=x
 
 // ---------------------------------------------------------------------------------
+// Sparse MoE FFN (mixtral; BASELINE configs[4]).  Restated from mlx_lm.models.mixtral.MixtralSparseMoeBlock +
+// switch_layers.SwitchGLU (oracle/llama_oracle.py moe_block has the rounding points); the reference hosts MoE
+// families through the same operator API (src/dnet/core/models/gpt_oss.py, deepseek_v2.py).  One token at a time
+// (T = 1): the experts a token uses are only known on the device, so the expert ops take a device table of expert
+// weight pointers and a device index instead of weight pointers -- the launch sequence is fixed, i.e. capturable.
+//   OpRouter      xn = RMSNorm(h);  logits[e] = T(xn . Wr[e])
+//   k_moe_select  the k largest logits (ties: lowest index), scores = T(softmax over those k, fp32 math)
+//   OpGateUpMoe   act_j = SwiGLU of expert sel[j]           (j = 0..k-1; same epilogue as the dense OpGateUp)
+//   OpDownMoe     y_j = T(act_j Wd[sel[j]]^T); term_j = T(y_j * score_j); acc = T(acc + term_j) in selection order;
+//                 the last j writes out = T(h + acc)
+// ---------------------------------------------------------------------------------
+struct OpRouter {
+  static constexpr int ALIGN = 1;
+  int K, nrows;                  // hidden, n_experts
+  const bf16 *x, *ln_w, *w;      // [H], [H], [E][H]
+  float* logits;                 // [E]
+  float eps;
+  __device__ __forceinline__ const bf16* row(int r) const { return w + (size_t)r * K; }
+  template <int T>
+  __device__ __forceinline__ void prologue(bf16* xs, float* scratch, float*) const {
+    stage_rmsnorm<T>(xs, scratch, x, ln_w, K, eps);
+  }
+  template <int T>
+  __device__ __forceinline__ void epilogue(int rb, int nv, int lane, float v, float*) const {
+    const int r_local = lane / T, t = lane % T;
+    if (r_local < nv) logits[(size_t)t * nrows + rb + r_local] = bf16r(v);
+  }
+  __device__ __forceinline__ void finish(float*) const {}
+};
+
+constexpr int MOE_MAX_E = 64, MOE_MAX_K = 8;
+__global__ void __launch_bounds__(32) k_moe_select(const float* __restrict__ logits, int E, int k, int32_t* __restrict__ sel,
+                                                   float* __restrict__ score) {
+  if (threadIdx.x != 0) return;
+  float v[MOE_MAX_K];
+  int id[MOE_MAX_K];
+  unsigned long long taken = 0ull;
+  for (int j = 0; j < k; ++j) {                    // selection in descending order, first index wins a tie
+    float best = -INFINITY; int bi = 0;
+    for (int e = 0; e < E; ++e)
+      if (!((taken >> e) & 1ull) && logits[e] > best) { best = logits[e]; bi = e; }
+    taken |= 1ull << bi;
+    v[j] = best; id[j] = bi;
+  }
+  float sum = 0.f, ex[MOE_MAX_K];
+  for (int j = 0; j < k; ++j) { ex[j] = expf(v[j] - v[0]); sum += ex[j]; }
+  for (int j = 0; j < k; ++j) { sel[j] = id[j]; score[j] = bf16r(ex[j] / sum); }
+}
+
+struct OpGateUpMoe {
+  static constexpr int ALIGN = 2;
+  int K, nrows;                        // hidden, 2*ffn
+  const bf16 *x, *ln_w;
+  const bf16* const* table;            // device: [3][E] expert pointers (gate, up, down)
+  const int32_t* sel; int j, E;
+  bf16* act;                           // [ffn] of selection j
+  float eps;
+  __device__ __forceinline__ const bf16* row(int vr) const {
+    // (clamped: with programmatic dependent launch the L2 pre-touch may run before k_moe_select has written sel)
+    const bf16* base = table[((vr & 1) ? E : 0) + min(max(__ldg(sel + j), 0), E - 1)];
+    return base + (size_t)(vr >> 1) * K;
+  }
+  template <int T>
+  __device__ __forceinline__ void prologue(bf16* xs, float* scratch, float*) const {
+    stage_rmsnorm<T>(xs, scratch, x, ln_w, K, eps);
+  }
+  template <int T>
+  __device__ __forceinline__ void epilogue(int rb, int nv, int lane, float v, float*) const {
+    const int r_local = lane / T, t = lane % T;
+    const int vr = rb + r_local;
+    const float y = bf16r(v);
+    const float u = __shfl_xor_sync(0xffffffffu, y, T);
+    if (r_local >= nv || (vr & 1)) return;
+    const float s = bf16r(1.0f / (1.0f + expf(-y)));
+    const float a = bf16r(__fmul_rn(y, s));
+    act[(size_t)t * (nrows >> 1) + (vr >> 1)] = __float2bfloat16_rn(__fmul_rn(a, u));
+  }
+  __device__ __forceinline__ void finish(float*) const {}
+};
+
+struct OpDownMoe {
+  static constexpr int ALIGN = 1;
+  int K, nrows;                        // ffn, hidden
+  const bf16* a;                       // [ffn] activation of selection j
+  const bf16* const* table;
+  const int32_t* sel; const float* score; int j, k, E;
+  float* ybuf;                         // [H] running T-rounded sum of the weighted expert outputs
+  const bf16* resid; bf16* out;        // [H]
+  __device__ __forceinline__ const bf16* row(int r) const {
+    return table[2 * E + min(max(__ldg(sel + j), 0), E - 1)] + (size_t)r * K;
+  }
+  template <int T>
+  __device__ __forceinline__ void prologue(bf16* xs, float*, float*) const { stage_copy<T>(xs, a, K); }
+  template <int T>
+  __device__ __forceinline__ void epilogue(int rb, int nv, int lane, float v, float*) const {
+    const int r_local = lane / T;
+    if (r_local >= nv) return;
+    const int idx = rb + r_local;
+    const float term = bf16r(__fmul_rn(bf16r(v), __ldg(score + j)));
+    const float acc = j == 0 ? term : bf16r(__fadd_rn(ybuf[idx], term));
+    if (j + 1 < k) ybuf[idx] = acc;
+    else out[idx] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(resid[idx]), acc));
+  }
+  __device__ __forceinline__ void finish(float*) const {}
+};
+
+// ---------------------------------------------------------------------------------
 // Op 5: final RMSNorm (last position) -> lm_head -> bf16 logits -> greedy sample
 //   Sampler.sample with temperature 0: argmax (first maximal index), logprob =
 //   T(v - T(logsumexp(v)))     (reference core/decoding/sampler.py:33-52)

@@ -99,6 +99,7 @@ struct MkParams {
   unsigned long long* dbg;   // optional [grid][n_layers][16] globaltimer stamps of CTA thread 0 (mk_debug)
   int scratch_bytes;      // shared scratch (activation vector / attention tiles)
   int attn_tc;               // 1: long-context attention phase on mma.sync with K/V tiles staged in shared memory (mk_attention_tc)
+  int attn_last;             // plain attention, S > 1: the last-arriving split CTA merges its head (else every CTA merges all heads while staging o_proj)
   int attn_single;           // plain attention: contexts up to this many tokens keep one CTA per head (no split merge)
   // quantised KV (dn_kvquant.cuh): 0 = bf16 pages; 4 / 8 = packed pages, two-pass attention
   int kv_bits;
@@ -806,6 +807,35 @@ __device__ __forceinline__ void mk_attention(const MkParams& p, const MkLayer& L
         if (d == 0) { pp[128] = M; pp[129] = Ls; }
       }
     }
+    if (S > 1 && p.attn_last) {
+      // the last split CTA of the head to arrive merges the head's S partials (split order -> the result does not depend
+      // on who merges) and writes the normalised bf16 head: the o_proj staging of all CTAs becomes a plain copy
+      __threadfence();
+      cbar_sync();
+      int* flag = reinterpret_cast<int*>(wpart + MK_CW * 132);
+      if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(p.tickets + head, 1u);
+        *flag = (old == (unsigned)S - 1u) ? 1 : 0;
+        if (*flag) p.tickets[head] = 0u;                       // re-armed for the next layer / launch
+      }
+      cbar_sync();
+      if (*flag && threadIdx.x < HD) {
+        __threadfence();
+        const int d = threadIdx.x;
+        const float* hp = p.part + ((size_t)head * p.nsplit) * PART_STRIDE;
+        float Mg = -INFINITY;
+        for (int s2 = 0; s2 < S; ++s2) Mg = fmaxf(Mg, __ldcg(hp + (size_t)s2 * PART_STRIDE + 128));
+        float Lg = 0.f, acc = 0.f;
+        for (int s2 = 0; s2 < S; ++s2) {
+          const float ms = __ldcg(hp + (size_t)s2 * PART_STRIDE + 128);
+          if (ms == -INFINITY) continue;
+          const float wgt = exp2f((ms - Mg) * LOG2E);
+          Lg = fmaf(__ldcg(hp + (size_t)s2 * PART_STRIDE + 129), wgt, Lg);
+          acc = fmaf(__ldcg(hp + (size_t)s2 * PART_STRIDE + d), wgt, acc);
+        }
+        p.attn[head * HD + d] = __float2bfloat16_rn(acc * (1.0f / Lg));
+      }
+    }
     cbar_sync();
   }
 }
@@ -1182,7 +1212,7 @@ __device__ __forceinline__ void mk_stage_attn_merge(bf16* xs, const MkParams& p)
   const int kv_len = p.st->pos + 1;
   int nact, tps;
   mk_attn_geometry(p, kv_len, nact, tps);
-  if (nact == 1 || MODE == MK_ATT_TC) {  // the attention CTAs already wrote the normalised heads
+  if (nact == 1 || MODE == MK_ATT_TC || (MODE == MK_ATT_PLAIN && p.attn_last)) {  // the attention CTAs already wrote the normalised heads
     mk_stage_copy(xs, p.attn, p.n_heads * HD);
     return;
   }

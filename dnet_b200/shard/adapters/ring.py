@@ -428,6 +428,20 @@ class RingAdapter(TopologyAdapter):
     # ------------------------------------------------------------------ leases + schedule (head shard)
     def lease(self, nonce: str, steps: int) -> None:
         """Head shard: allow ``steps`` more on-device decode steps for ``nonce`` (thread-safe)."""
+        if not getattr(self.runtime, "use_megakernel", True):
+            # the device-closed loop lives in the persistent step kernel; models that run on the per-op path (sparse
+            # MoE) are driven by the host-closed loop.  Answer with an error token so the API does not wait.
+            logger.error("Shard %s: lease for nonce %s refused: this model does not run in the step kernel "
+                         "(use the host-closed token loop)", self.runtime.shard_id, nonce)
+            ctx = self._streams.lane_ctx(nonce)
+            cb = ctx.params.get("callback_url", "") if ctx is not None else ""
+            rt = self.runtime
+            rt.activation_send_queue.put(ActivationMessage(
+                nonce=nonce, pool_id=-1, batch_size=1, shape=(1,), dtype=rt._wire_dtype_str, layer_id=-1,
+                timestamp=utc_epoch_now(), node_origin=f"shard_{rt.shard_id}", callback_url=cb, is_final=True,
+                token_id=-1099, logprob=0.0, top_logprobs={}))
+            return
+
         def _add():
             self._leases[nonce] = self._leases.get(nonce, 0) + int(steps)
             if self._lease_evt is not None:

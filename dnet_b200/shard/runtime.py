@@ -287,6 +287,10 @@ class ShardRuntime:
                                     kv_pool_pages=pages, wire_dtype=self._wire_dtype_str, kv_bits=kv_bits,
                                     kv_group=int(self.kv_cache_config.group_size))
         self.model.apply_quantization_from_config(self.model_metadata.model_config, model_metadata=self.model_metadata)
+        if not getattr(self.model, "step_kernel_ok", True):
+            # e.g. sparse MoE: expert selection happens on the device, the layers run on the per-op path (CUDA graphs)
+            self.use_megakernel = False
+            self.use_cuda_graphs = True
         # embed / norm / head iff this shard owns layer 0 / the last layer (reference runtime.py:263-273)
         has_start = 0 in self.assigned_layers
         has_end = (self.model_metadata.num_layers - 1) in self.assigned_layers

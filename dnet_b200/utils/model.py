@@ -188,9 +188,16 @@ class SyntheticSource:
             self._shapes[p + "self_attn.k_proj.weight"] = (kd, H)
             self._shapes[p + "self_attn.v_proj.weight"] = (kd, H)
             self._shapes[p + "self_attn.o_proj.weight"] = (H, qd)
-            self._shapes[p + "mlp.gate_proj.weight"] = (F_, H)
-            self._shapes[p + "mlp.up_proj.weight"] = (F_, H)
-            self._shapes[p + "mlp.down_proj.weight"] = (H, F_)
+            if int(c.get("num_local_experts", 0) or 0) > 0:       # sparse MoE FFN (mixtral checkpoint names)
+                self._shapes[p + "block_sparse_moe.gate.weight"] = (int(c["num_local_experts"]), H)
+                for e in range(int(c["num_local_experts"])):
+                    self._shapes[p + f"block_sparse_moe.experts.{e}.w1.weight"] = (F_, H)
+                    self._shapes[p + f"block_sparse_moe.experts.{e}.w3.weight"] = (F_, H)
+                    self._shapes[p + f"block_sparse_moe.experts.{e}.w2.weight"] = (H, F_)
+            else:
+                self._shapes[p + "mlp.gate_proj.weight"] = (F_, H)
+                self._shapes[p + "mlp.up_proj.weight"] = (F_, H)
+                self._shapes[p + "mlp.down_proj.weight"] = (H, F_)
             self._shapes[p + "input_layernorm.weight"] = (H,)
             self._shapes[p + "post_attention_layernorm.weight"] = (H,)
         self._shapes["model.embed_tokens.weight"] = (V, H)
@@ -216,7 +223,7 @@ class SyntheticSource:
             return
         g = torch.Generator(device=dst.device)
         g.manual_seed(self.seed * 1000003 + self._names.index(name))
-        std = 1.0 if name == "model.embed_tokens.weight" else self.std
+        std = 1.0 if name == "model.embed_tokens.weight" or name.endswith("block_sparse_moe.gate.weight") else self.std
         # generate in fp32 chunks to bound temporary memory
         flat = dst.view(-1)
         step = 1 << 26

@@ -73,6 +73,8 @@ typedef struct dn_model_cfg {
   int32_t kv_bits;         /* 0: 16-bit KV (mlx_lm KVCache); 4 / 8: affine-quantised KV (QuantizedKVCache,
                               reference utils/model.py:505-554 -- the API's default kv_bits) */
   int32_t kv_group;        /* quantisation group along head_dim: 64 */
+  int32_t n_experts;       /* 0: dense MLP; > 0: sparse MoE FFN (mixtral num_local_experts; BASELINE configs[4]) */
+  int32_t top_k;           /* experts per token (num_experts_per_tok) */
 } dn_model_cfg;
 
 /* ---- process / device -------------------------------------------------- */
@@ -100,6 +102,11 @@ int dn_model_create(const dn_model_cfg* cfg, const int32_t* abs_layers, int n_la
                     const float* inv_freq_host /* head_dim/2 fp32 */, dn_model** out);
 int dn_model_destroy(dn_model* m);
 int dn_bind_layer(dn_model* m, int abs_layer, const void* const* dev_ptrs /* DN_W_COUNT */);
+/* sparse MoE layers (cfg.n_experts > 0; mlx_lm.models.mixtral via the same BaseRingModel seam the reference uses for
+ * its MoE families, core/models/gpt_oss.py, deepseek_v2.py): router [E][H] and per-expert gate / up / down matrices.
+ * dn_bind_layer still binds the attention tensors and norms (its gate/up/down entries may be NULL for such a model). */
+int dn_bind_layer_experts(dn_model* m, int abs_layer, const void* router, const void* const* gate /* [E] */,
+                          const void* const* up /* [E] */, const void* const* down /* [E] */, int n_experts);
 int dn_unbind_layer(dn_model* m, int abs_layer);
 int dn_layer_is_bound(dn_model* m, int abs_layer);
 /* embed_tokens / final norm / lm_head (reference shard/runtime.py:263-273); any may be NULL */

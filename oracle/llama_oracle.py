@@ -66,6 +66,8 @@ class OracleConfig:
     rope_scaling: Optional[dict] = None
     tie_word_embeddings: bool = False
     attention_bias: bool = False  # qwen2-style QKV bias
+    num_local_experts: int = 0    # mixtral: experts per MoE layer (0 = dense MLP)
+    num_experts_per_tok: int = 2
 
     @classmethod
     def from_dict(cls, d: dict) -> "OracleConfig":
@@ -83,6 +85,8 @@ class OracleConfig:
             rope_scaling=d.get("rope_scaling"),
             tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
             attention_bias=bool(d.get("attention_bias", False)),
+            num_local_experts=int(d.get("num_local_experts", 0) or 0),
+            num_experts_per_tok=int(d.get("num_experts_per_tok", 2) or 2),
         )
 
 
@@ -336,6 +340,9 @@ class LlamaOracle:
         r = self.linear(a, p + "self_attn.o_proj.weight")
         h = self.T(x.to(torch.float32) + r.to(torch.float32))
         hn = self.rms_norm(h, p + "post_attention_layernorm.weight")
+        if c.num_local_experts:
+            d = self.moe_block(hn, p + "block_sparse_moe.")
+            return self.T(h.to(torch.float32) + d.to(torch.float32))
         g = self.linear(hn, p + "mlp.gate_proj.weight").to(torch.float32)
         u = self.linear(hn, p + "mlp.up_proj.weight").to(torch.float32)
         s = self.T(torch.sigmoid(g)).to(torch.float32)
@@ -343,6 +350,44 @@ class LlamaOracle:
         m = self.T(act * u)
         d = self.linear(m, p + "mlp.down_proj.weight")
         return self.T(h.to(torch.float32) + d.to(torch.float32))
+
+
+    def moe_block(self, hn: torch.Tensor, p: str) -> torch.Tensor:
+        """Sparse MoE FFN restated from mlx_lm.models.mixtral.MixtralSparseMoeBlock + switch_layers.SwitchGLU
+        (mlx-lm 0.28.2; not in /root/reference -- PARITY UNPINNED like the rest of this file).  The reference hosts
+        MoE families through the same BaseRingModel operator API (core/models/gpt_oss.py, deepseek_v2.py); mixtral is
+        BASELINE.json configs[4].
+
+          gates  = gate(x)                                   Linear, logits rounded to T
+          inds   = argpartition(-gates, k-1)[..., :k]        the k largest logits (ties: lowest index first here)
+          scores = softmax(gates[inds], precise=True)        fp32 math over the k selected logits, rounded to T
+          y_e    = down_e(silu(gate_e(x)) * up_e(x))         per selected expert, SwiGLU temporaries in T as in the dense MLP
+          y      = sum_e T(y_e * score_e)                    elementwise product rounded to T, then the sum over k rounded
+                                                             to T (k = 2: one addition; selection order = descending logit)
+        """
+        c = self.cfg
+        E, k = c.num_local_experts, c.num_experts_per_tok
+        gates = self.linear(hn, p + "gate.weight").to(torch.float32)                 # [T, E]
+        top = torch.sort(gates, dim=-1, descending=True, stable=True)
+        inds = top.indices[:, :k]
+        sel = top.values[:, :k]
+        scores = self.T(torch.softmax(sel, dim=-1)).to(torch.float32)                # [T, k]
+        out = torch.zeros(hn.shape[0], c.hidden_size, dtype=torch.float32)
+        for t in range(hn.shape[0]):
+            acc = None
+            for j in range(k):
+                e = int(inds[t, j])
+                x1 = hn[t:t + 1]
+                g = self.linear(x1, f"{p}experts.{e}.w1.weight").to(torch.float32)
+                u = self.linear(x1, f"{p}experts.{e}.w3.weight").to(torch.float32)
+                s_ = self.T(torch.sigmoid(g)).to(torch.float32)
+                act = self.T(g * s_).to(torch.float32)
+                m = self.T(act * u)
+                y = self.linear(m, f"{p}experts.{e}.w2.weight").to(torch.float32)[0]
+                term = self.T(y * scores[t, j]).to(torch.float32)
+                acc = term if acc is None else self.T(acc + term).to(torch.float32)
+            out[t] = acc
+        return self.T(out)
 
 
 @dataclass
@@ -441,9 +486,17 @@ def make_weights(cfg: OracleConfig, seed: int, layers: Optional[Sequence[int]] =
         w[p + "self_attn.k_proj.weight"] = rnd(b + 1, (kd, H))
         w[p + "self_attn.v_proj.weight"] = rnd(b + 2, (kd, H))
         w[p + "self_attn.o_proj.weight"] = rnd(b + 3, (H, qd))
-        w[p + "mlp.gate_proj.weight"] = rnd(b + 4, (F_, H))
-        w[p + "mlp.up_proj.weight"] = rnd(b + 5, (F_, H))
-        w[p + "mlp.down_proj.weight"] = rnd(b + 6, (H, F_))
+        if cfg.num_local_experts:
+            w[p + "block_sparse_moe.gate.weight"] = rnd(b + 12, (cfg.num_local_experts, H), 1.0)   # wide logits: clear top-k
+            for e in range(cfg.num_local_experts):
+                eb = 100000 + 4096 * l + 8 * e
+                w[p + f"block_sparse_moe.experts.{e}.w1.weight"] = rnd(eb + 0, (F_, H))
+                w[p + f"block_sparse_moe.experts.{e}.w3.weight"] = rnd(eb + 1, (F_, H))
+                w[p + f"block_sparse_moe.experts.{e}.w2.weight"] = rnd(eb + 2, (H, F_))
+        else:
+            w[p + "mlp.gate_proj.weight"] = rnd(b + 4, (F_, H))
+            w[p + "mlp.up_proj.weight"] = rnd(b + 5, (F_, H))
+            w[p + "mlp.down_proj.weight"] = rnd(b + 6, (H, F_))
         # norm weights near 1 but not exactly 1 so the second rounding is exercised
         w[p + "input_layernorm.weight"] = (1.0 + rnd(b + 7, (H,), 0.1).to(torch.float32)).to(dtype)
         w[p + "post_attention_layernorm.weight"] = (1.0 + rnd(b + 8, (H,), 0.1).to(torch.float32)).to(dtype)

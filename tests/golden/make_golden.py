@@ -32,6 +32,10 @@ TINY_B = dict(hidden_size=512, num_attention_heads=8, num_key_value_heads=2, hea
               tie_word_embeddings=True, attention_bias=True, torch_dtype="bfloat16",
               rope_scaling=dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
                                 original_max_position_embeddings=64))
+# sparse MoE FFN (mixtral): 8 experts, top-2, GQA group 2
+TINY_MOE = dict(hidden_size=512, num_attention_heads=4, num_key_value_heads=2, head_dim=128, intermediate_size=768,
+                vocab_size=1024, num_hidden_layers=3, rms_norm_eps=1e-5, rope_theta=1000000.0, model_type="mixtral",
+                tie_word_embeddings=False, torch_dtype="bfloat16", num_local_experts=8, num_experts_per_tok=2)
 MARGIN_ULPS = 3.0
 
 
@@ -97,3 +101,4 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     search("tiny_llama", TINY, wseed=11, prompt_len=7, steps=16)
     search("tiny_qwen2_tied", TINY_B, wseed=23, prompt_len=70, steps=10)
+    search("tiny_mixtral", TINY_MOE, wseed=31, prompt_len=21, steps=10)

@@ -114,6 +114,6 @@ def test_quantised_kv_pool_is_smaller(cuda_lib):
     from dnet_b200 import _cabi
     import ctypes as C
 
-    assert C.sizeof(_cabi.ModelCfg) == 15 * 4
+    assert C.sizeof(_cabi.ModelCfg) == 17 * 4
     unit = {8: 64 * 128 + 64 * 8, 4: 64 * 64 + 64 * 8}
     assert unit[8] * 2 * 8 / 64 == 2176 and unit[4] * 2 * 8 / 64 == 1152

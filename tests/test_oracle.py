@@ -53,6 +53,59 @@ def test_structure_matches_hf_llama_fp32():
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
 
 
+def test_moe_structure_matches_hf_mixtral_fp32():
+    """The restated sparse-MoE block (router -> top-k -> softmax over the selected logits -> SwiGLU experts ->
+    weighted sum) against an independent implementation of the same architecture."""
+    transformers = pytest.importorskip("transformers")
+    if not hasattr(transformers, "MixtralForCausalLM"):
+        pytest.skip("this transformers build has no Mixtral")
+    cfgd = dict(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, head_dim=128, intermediate_size=384,
+                vocab_size=320, num_hidden_layers=2, rms_norm_eps=1e-5, rope_theta=1000000.0, num_local_experts=8,
+                num_experts_per_tok=2)
+    cfg = OracleConfig.from_dict(cfgd)
+    w = make_weights(cfg, 9, dtype=torch.float32)
+    hc = transformers.MixtralConfig(**cfgd, max_position_embeddings=512, tie_word_embeddings=False, sliding_window=None,
+                                    attn_implementation="eager", router_jitter_noise=0.0)
+    m = transformers.MixtralForCausalLM(hc).eval().to(torch.float32)
+    sd = m.state_dict()
+    if any(".experts.gate_up_proj" in k for k in sd):       # newer transformers keep the experts stacked
+        mapped = {}
+        for k in sd:
+            if k.endswith("mlp.experts.gate_up_proj") or k.endswith("block_sparse_moe.experts.gate_up_proj"):
+                pre = k.rsplit("experts.", 1)[0].replace(".mlp.", ".block_sparse_moe.")
+                g = torch.stack([w[f"{pre}experts.{e}.w1.weight"] for e in range(8)])
+                u = torch.stack([w[f"{pre}experts.{e}.w3.weight"] for e in range(8)])
+                t = torch.cat([g, u], dim=1)
+                mapped[k] = t if t.shape == sd[k].shape else t.transpose(1, 2).contiguous()
+            elif k.endswith("experts.down_proj"):
+                pre = k.rsplit("experts.", 1)[0].replace(".mlp.", ".block_sparse_moe.")
+                t = torch.stack([w[f"{pre}experts.{e}.w2.weight"] for e in range(8)])
+                mapped[k] = t if t.shape == sd[k].shape else t.transpose(1, 2).contiguous()
+            elif ".mlp.gate.weight" in k:
+                mapped[k] = w[k.replace(".mlp.gate.", ".block_sparse_moe.gate.")]
+            else:
+                mapped[k] = w[k]
+        m.load_state_dict(mapped)
+    else:
+        m.load_state_dict({k: w[k] for k in sd})
+    ids = torch.randint(0, 320, (1, 9), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = m(ids).logits[0]
+    o = LlamaOracle(cfg, w, torch.float32)
+    kv = {l: OracleKV() for l in range(2)}
+    x = o.embed(ids[0, :5])
+    for l in range(2):
+        x = o.apply_single_layer(l, x, kv[l])
+    outs = [o.lm_project(o.normalize(x))]
+    for t in range(5, 9):
+        x = o.embed(ids[0, t:t + 1])
+        for l in range(2):
+            x = o.apply_single_layer(l, x, kv[l])
+        outs.append(o.lm_project(o.normalize(x)))
+    got = torch.cat(outs)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
 def test_llama3_rope_scaling_matches_hf():
     transformers = pytest.importorskip("transformers")
     from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
@@ -70,7 +123,7 @@ def test_llama3_rope_scaling_matches_hf():
     assert torch.allclose(mine, ref.float(), rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("name", ["tiny_llama", "tiny_qwen2_tied"])
+@pytest.mark.parametrize("name", ["tiny_llama", "tiny_qwen2_tied", "tiny_mixtral"])
 def test_oracle_matches_golden(name):
     g = load_golden(name)
     cfg = OracleConfig.from_dict(g["config"])
