@@ -416,6 +416,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if args.config == "swap":
         from bench_swap import run_swap
         return run_swap(args, rank, local_rank, world)
+    if args.config == "moe":
+        from bench_moe import run_moe
+        return run_moe(args, rank, local_rank, world)
     if args.config == "prefill":
         from bench_prefill import run_prefill
         return run_prefill(args, rank, local_rank, world)
@@ -467,7 +470,7 @@ def main():
                     help="N>1: lm_head tensor-parallel over the ring's shards (auto: rings of >= 4 shards)")
     ap.add_argument("--sched-rounds", type=int, default=8, help="decode rounds per schedule frame (head shard's RingAdapter)")
     ap.add_argument("--sched-depth", type=int, default=4, help="schedule frames in flight")
-    ap.add_argument("--config", default="decode", choices=["decode", "swap", "prefill"],
+    ap.add_argument("--config", default="decode", choices=["decode", "swap", "prefill", "moe"],
                     help="decode: BASELINE configs[1] (the bench contract); swap: configs[3], Llama-3-70B layer swap (bench_swap.py)")
     ap.add_argument("--prefill-len", type=int, default=32768, help="--config prefill: prompt tokens")
     ap.add_argument("--prefill-chunk", type=int, default=512, help="--config prefill: tokens per chunk frame")

@@ -209,6 +209,10 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    import gc
+    gc.collect()
+    gc.freeze()                 # a serving process does the same: no stop-the-world collection of the (large, static) heap
+    gc.disable()                # inside a request's latency path
     l0 = lib.dn_launch_count()
     h0, n0 = pol.sched_host_s, pol.sched_host_entries
     stamp0 = len(stamps)
@@ -216,6 +220,7 @@ def run_ring(args, rank: int, local_rank: int, world: int) -> None:
     ms_local, wall = run_steps(K, 1 + W, W * NS, True)
     host_us = (pol.sched_host_s - h0) / max(1, pol.sched_host_entries - n0) * 1e6
     tw1 = time.perf_counter()
+    gc.enable()
     launches = int(lib.dn_launch_count() - l0)
     step_err = int(lib.dn_step_error(rt.model._h, rt.compute_stream_ptr))
 

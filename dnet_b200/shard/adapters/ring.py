@@ -514,7 +514,10 @@ class RingAdapter(TopologyAdapter):
                     await self._lease_evt.wait()
                     # leases of concurrent requests arrive as separate frames within a few hundred microseconds: collect
                     # them before fixing the order, or the first request would be scheduled alone (bubble-padded rounds)
-                    await asyncio.sleep(self.lease_grace_s)
+                    # (nothing to wait for when every request that holds a lane here has its lease already)
+                    waiting = [n for n in self._streams.lanes_in_use() if self._leases.get(n, 0) <= 0]
+                    if waiting:
+                        await asyncio.sleep(self.lease_grace_s)
                 if not self.is_head:
                     self._leases.clear()
                     continue

@@ -89,7 +89,10 @@ def test_r02_our_arm_line(name, n):
     if n == 1:
         assert r["traffic"] and 0.99 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.05
         od = d["check"]["oracle_full_depth"]
-        assert od and od["compared"] >= 8 and od["equal_prefix"] >= 1
+        # full depth (32 layers, the GPU arm's own weights), the oracle teacher-forced with the GPU's tokens:
+        # every GPU token is the oracle's argmax or within 2 bf16 ulps of the oracle's best logit
+        assert od and od["compared"] >= 8 and od["pass"] is True and od["max_regret_ulps"] <= 2.0
+        assert od["identical"] >= od["compared"] - len(od["mismatch_steps"])
     else:
         assert d["ring_hop_us"]["activation_8k"] > 0
 

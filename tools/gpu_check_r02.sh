@@ -12,3 +12,6 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_shard_step' -s 4 -c 1 -o gpurun_out/r02_prof_step python bench.py --steps 4 --warmup 3 --no-cpu --no-single > gpurun_out/r02_ncu_step.log 2>&1; tail -2 gpurun_out/r02_ncu_step.log | cut -c1-300
   ncu -i gpurun_out/r02_prof_step.ncu-rep --page raw --csv > gpurun_out/r02_ncu_step_raw.csv 2>/dev/null; wc -l gpurun_out/r02_ncu_step_raw.csv
 fi
+# driver settings (what the round-end bench runs) and the MoE config on one GPU
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_k20.json 2> gpurun_out/r02_bench_n1_k20.err; python -c "import json; d=json.load(open('gpurun_out/r02_bench_n1_k20.json')); print('K=20', d['value'], d['e2e']['value'], d['roofline']['frac'], d.get('check',{}).get('oracle_full_depth'))" | cut -c1-900
+timeout 600 python bench.py --config moe --steps 32 --warmup 4 --in-flight 4 > gpurun_out/r02_bench_moe_n1.json 2> gpurun_out/r02_bench_moe_n1.err; tail -2 gpurun_out/r02_bench_moe_n1.err | cut -c1-400; head -c 700 gpurun_out/r02_bench_moe_n1.json; echo
