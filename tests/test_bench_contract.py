@@ -99,7 +99,8 @@ def test_r02_our_arm_line(name, n):
 
 def test_r02_same_token_at_every_shard_count():
     toks = set()
-    for name in ("r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"):
+    # the driver's settings (--steps 20 --warmup 5) at every N: request 0's token after 25 decode steps
+    for name in ("r02_bench_n1_k20.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"):
         d = _load(name)
         toks.add((d["check"]["nonce0_token_after_steps"], d["check"]["token"]))
     assert len(toks) == 1, toks
