@@ -33,7 +33,8 @@ def _oracle_tokens(cfgd, w, prompt, steps):
     return toks, logits, gaps
 
 
-@pytest.mark.parametrize("name,plen", [("tiny_llama", 37), ("tiny_llama", 1500), ("tiny_qwen2_tied", 130), ("tiny_qwen2_tied", 700)])
+@pytest.mark.parametrize("name,plen", [("tiny_llama", 37), ("tiny_llama", 1500), ("tiny_qwen2_tied", 130), ("tiny_qwen2_tied", 700),
+                                       ("tiny_llama", 2100), ("tiny_llama", 8200)])
 def test_tensor_core_decode_attention_against_oracle_and_cuda_core_path(cuda_lib, name, plen):
     g = load_golden(name)
     cfgd = g["config"]
@@ -48,7 +49,7 @@ def test_tensor_core_decode_attention_against_oracle_and_cuda_core_path(cuda_lib
         for tc in (1, 0):
             cuda_lib.dn_set_option(b"attn_tc", tc)
             cuda_lib.dn_set_option(b"attn_tc_min", 16)
-            rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]), megakernel=True, cuda_graphs=False, max_tokens=2048)
+            rt = make_runtime(cfgd, w, range(cfgd["num_hidden_layers"]), megakernel=True, cuda_graphs=False, max_tokens=max(2048, plen + 64))
             try:
                 ids, out = prompt, []
                 for step in range(steps):

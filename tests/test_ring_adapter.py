@@ -607,3 +607,50 @@ def test_tp_head_schedule_keeps_a_requests_steps_S_plus_1_entries_apart_and_flus
         # every real entry's token is merged by the head at entry j + S, which exists in the stream
         assert all(i + S < len(stream) for i, _, _ in real)
         assert fr.unpack_sched(fr.pack_sched(stream)) == stream                 # bubbles survive the wire format
+
+
+def test_lease_is_refused_with_an_error_token_when_the_model_cannot_run_in_the_step_kernel(grpc_ok):
+    """Sparse-MoE models run on the per-op path (runtime.use_megakernel False): the device-closed loop does not exist
+    for them, so a lease is answered at once with a negative token instead of leaving the API waiting."""
+    ad, rt = make_adapter(assigned_next={0})
+    rt.use_megakernel = False
+    ad._streams.configure_lanes(2)
+    ctx = ad._streams.claim_lane("m")
+    ctx.params.update(seq0=1, callback_url="grpc://127.0.0.1:9")
+
+    async def main():
+        await ad.start()
+        ad.lease("m", 4)
+        assert "m" not in ad._leases
+        msg = rt.activation_send_queue.get_nowait()
+        assert msg.is_final and msg.token_id <= -1000 and msg.nonce == "m" and msg.callback_url == "grpc://127.0.0.1:9"
+        await ad.shutdown()
+
+    asyncio.run(main())
+
+
+def test_single_request_is_scheduled_without_the_collection_grace(grpc_ok):
+    """The head waits lease_grace_s after the first lease only while another lane-holding request has none yet."""
+    ad, rt = make_adapter(assigned_next={0})
+    ad.lease_grace_s = 1.0
+    ad.rounds_per_frame, ad.sched_depth = 1, 4
+    ad._streams.configure_lanes(4)
+    ad._streams.claim_lane("solo").params["seq0"] = 1
+
+    async def main():
+        await ad.start()
+        t0 = asyncio.get_running_loop().time()
+        ad.lease("solo", 1)
+        assert await wait_until(lambda: rt.activation_recv_queue.qsize() >= 1, timeout=0.8), "scheduled only after the grace"
+        assert asyncio.get_running_loop().time() - t0 < 0.8
+        rt.activation_recv_queue.get_nowait().sched_done.record(None)
+        # a second request holds a lane but has no lease yet: now the grace applies
+        ad._streams.claim_lane("other").params["seq0"] = 1
+        await asyncio.sleep(0.05)
+        t1 = asyncio.get_running_loop().time()
+        ad.lease("solo", 1)
+        assert await wait_until(lambda: rt.activation_recv_queue.qsize() >= 1, timeout=5.0)
+        assert asyncio.get_running_loop().time() - t1 >= 0.9
+        await ad.shutdown()
+
+    asyncio.run(main())
