@@ -318,3 +318,33 @@ def test_mlx_quantised_checkpoint_dequantises_at_load(bits):
     bad["model.layers.0.mlp.down_proj.weight"] = torch.zeros(128, 24, dtype=torch.int32)      # 3-bit-like width
     with pytest.raises(ValueError):
         get_model_metadata(HostDictSource(bad, cfg))
+
+
+def test_mixtral_checkpoint_names_flow_through_metadata_layout_and_repack(tmp_path):
+    """Sparse-MoE checkpoints (HF mixtral names) are ordinary layer tensors for the loader: metadata, the pinned layer
+    record (256-byte aligned offsets), the repacked per-layer file and the synthetic source agree on the tensor set."""
+    from dnet_b200.utils.layer_manager import LayerManager
+    from dnet_b200.utils.model import HostDictSource, SyntheticSource, get_model_metadata
+    from oracle.llama_oracle import OracleConfig, make_weights
+
+    cfgd = dict(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, head_dim=128, intermediate_size=256,
+                vocab_size=64, num_hidden_layers=2, model_type="mixtral", num_local_experts=4, num_experts_per_tok=2)
+    w = make_weights(OracleConfig.from_dict(cfgd), 3)
+    m1 = get_model_metadata(HostDictSource(w, cfgd))
+    m2 = get_model_metadata(SyntheticSource(cfgd, seed=0))
+    assert m1.model_type == "mixtral" and set(m1.weight_info) == set(m2.weight_info) == {0, 1}
+    want = {"block_sparse_moe.gate.weight"} | {f"block_sparse_moe.experts.{e}.{k}.weight" for e in range(4) for k in ("w1", "w2", "w3")}
+    for m in (m1, m2):
+        suffixes = set(m.weight_info[1])
+        assert want <= suffixes and "mlp.gate_proj.weight" not in suffixes
+        assert {k: tuple(v.shape) for k, v in m.weight_info[1].items() if k in want} == \
+               {k: ((4, 256) if k.endswith("gate.weight") else ((256, 256))) for k in want}
+    lm = LayerManager(m1, [1], stage_host=True)
+    rec = lm._host_record(1)
+    views = lm.views(1, rec)
+    for e in range(4):
+        for k in ("w1", "w2", "w3"):
+            name = f"block_sparse_moe.experts.{e}.{k}.weight"
+            assert torch.equal(views[f"layers.1.{name}"], w[f"model.layers.1.{name}"])
+    assert torch.equal(views["layers.1.block_sparse_moe.gate.weight"], w["model.layers.1.block_sparse_moe.gate.weight"])
+    assert all(e.offset % 256 == 0 for e in lm._layout[1])
