@@ -57,3 +57,17 @@ def test_flag_travels_in_the_unchanged_proto():
         assert req.activation.batch_size == (0 if more else 1)
         back = ActivationMessage.from_proto(req, pool_id=-1)
         assert more_chunks_follow(back) is more
+
+
+def test_request_metrics_have_the_reference_keys():
+    """reference api/inference.py:216-233 (ChatResponseModel.metrics when profile=true)"""
+    ad = _FakeAdapter()
+    mgr = InferenceManager(ad, "local://")
+    m = {}
+
+    async def go():
+        return [r async for r in mgr.generate_stream("n", [1, 2, 3], 4, device_loop=False, metrics=m)]
+    out = asyncio.run(go())
+    assert len(out) == 4
+    assert set(m) == {"total_ms", "ttfb_ms", "token_gen_ms", "tokens_generated", "tps_overall", "tps_decoding"}
+    assert m["tokens_generated"] == 4 and m["total_ms"] >= m["ttfb_ms"] >= 0 and m["tps_decoding"] >= m["tps_overall"] > 0
